@@ -1,0 +1,139 @@
+/*
+ * idc_b200.h -- C ABI of the B200-native Local Hints Network forward
+ * (interactive deep colorization hot path).
+ *
+ * The reference has NO native interface: its operator boundary for this path is the
+ * Python call
+ *     self.net.forward(img_l_mc, input_ab_mc, input_mask_mult, mask_cent)
+ *         /root/reference/data/colorize_image.py:263   (ColorizeImageTorch.net_forward)
+ *         /root/reference/data/colorize_image.py:308   (ColorizeImageTorchDist.net_forward)
+ *     implemented by SIGGRAPHGenerator.forward
+ *         /root/reference/models/pytorch/model.py:134-175
+ * and, for the Caffe backend, the blob write + net.forward() at
+ *         /root/reference/data/colorize_image.py:425-431, 452-463.
+ * Every entry point below names the reference statement it replaces.  Plain pointers
+ * and sizes only (no torch types); see INTEGRATION.md for the ctypes binding.
+ *
+ * Conventions
+ *   - return value: 0 = IDC_OK, <0 = error (idc_last_error gives the text).
+ *   - all image tensors are FP32, NCHW, contiguous (the reference's layout:
+ *     model.py:139-141 builds [1,C,H,W] from numpy [C,H,W]).
+ *   - idc_forward takes DEVICE pointers and is asynchronous on `stream`;
+ *     idc_forward_host takes HOST pointers, copies through pinned staging buffers and
+ *     returns after the results are in host memory.
+ *   - a ctx is bound to one device, is not thread-safe, and owns packed weights +
+ *     activation workspace.  Callers own all I/O buffers.
+ *   - H and W must be multiples of 8 (three ::2 subsamplings + three x2 deconvs,
+ *     model.py:149-151, :75,:86,:96).
+ */
+#ifndef IDC_B200_H_
+#define IDC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct idc_ctx idc_ctx;
+
+enum {
+  IDC_OK = 0,
+  IDC_ERR_ARG = -1,          /* bad argument / null pointer / bad shape            */
+  IDC_ERR_CUDA = -2,         /* a CUDA call or kernel failed                        */
+  IDC_ERR_STATE = -3,        /* wrong call order (e.g. forward before finalize)     */
+  IDC_ERR_KEY = -4,          /* unknown / missing state_dict key                    */
+  IDC_ERR_UNSUPPORTED = -5,  /* e.g. not an sm_100 device                           */
+  IDC_ERR_WATCHDOG = -6      /* a device-side pipeline wait timed out               */
+};
+
+/* idc_create flags */
+enum {
+  IDC_FLAG_DIST = 1u << 0,        /* also run model_class + softmax (model.py:159-160)           */
+  IDC_FLAG_ENGINE_SIMT = 1u << 1, /* FP32 CUDA-core engine (exact FP32, slow); default = tcgen05 */
+  IDC_FLAG_FAST_FP16 = 1u << 2,   /* single-pass FP16 operands (1 MMA / product, ~6e-2 ab error);
+                                     default = 2-term split FP16 (3 MMAs / product, <=1e-3)      */
+  IDC_FLAG_GLOBAL_HINTS = 1u << 3,/* global-hints branch (models/global_model/deploy_nodist.prototxt:38-172,501-527) */
+  IDC_FLAG_NO_GRAPH = 1u << 4,    /* do not capture the forward into a CUDA graph               */
+  IDC_FLAG_KEEP_CONV10 = 1u << 5  /* materialise conv10_2 (debug); default fuses model_out into model10.1 */
+};
+
+/* dtype codes for idc_load_tensor */
+enum { IDC_F32 = 0, IDC_F64 = 1, IDC_I64 = 2 };
+
+/* Library / build info: "idc_b200 <version> sm_100a ..." */
+const char* idc_version(void);
+
+/* Replaces `model.SIGGRAPHGenerator(dist=dist)` + `.cuda()` + `.eval()`
+ * (data/colorize_image.py:221,230-232).  max_n = largest batch a forward may carry. */
+int idc_create(int device, int max_n, int h, int w, unsigned flags, idc_ctx** out);
+
+/* Replaces one entry of `self.net.load_state_dict(state_dict)` (data/colorize_image.py:229).
+ * key = reference state_dict key ("model1.0.weight", "model1.4.running_var", ...; conv OIHW,
+ * deconv IOHW, model.py:13-108).  Extra keys accepted with IDC_FLAG_GLOBAL_HINTS:
+ * "glob.{0,1,2,3}.weight/bias" + "glob.{0..3}.bn.*".  data is HOST memory. */
+int idc_load_tensor(idc_ctx* ctx, const char* key, const void* data, int dtype, int ndim,
+                    const int64_t* dims);
+
+/* Packs every loaded tensor into the device-resident weight arena (K-major FP16 hi/lo
+ * tiles for tcgen05, FP32 [K][Cout] for the SIMT engine; BatchNorm folded to scale/shift).
+ * Fails with IDC_ERR_KEY if a required key is missing. */
+int idc_finalize_weights(idc_ctx* ctx);
+
+/* Device pointer + size of the packed arena: rank 0 broadcasts it once over NCCL
+ * (SURVEY 8e); ranks != 0 call idc_adopt_weights() after receiving into it. */
+int idc_weights_arena(idc_ctx* ctx, void** dev_ptr, size_t* bytes);
+int idc_reserve_weights(idc_ctx* ctx);    /* allocate the arena without packing (receiver side) */
+int idc_adopt_weights(idc_ctx* ctx);      /* mark a received arena as final                     */
+
+/* Replaces `self.net.forward(img_l_mc, input_ab_mc, input_mask_mult, mask_cent)`
+ * (data/colorize_image.py:263 / :308), batched.
+ *   L_mc  [n,1,h,w]  L-50 in [-50,50]        ab [n,2,h,w] in [-110,110]
+ *   mask  [n,1,h,w]  in [0,1]                maskcent: model.py:142
+ *   glob  [n,316] or NULL: [313 ab histogram, 1 indicator, 1 mean saturation, 1 indicator]
+ *         (data/colorize_image.py:452-463; deploy_nodist.prototxt:8-18)
+ *   out_ab   [n,2,h,w]  tanh*110 (model.py:175).  NOTE the reference's dist=True return is
+ *            tanh*110*110 (model.py:166-168, quirk q1); the Python mirror applies that.
+ *   out_dist [n,529,h/4,w/4] or NULL: softmax(0.2*model_class(conv8_3)) BEFORE the nearest
+ *            x4 upsample (model.py:160); requires IDC_FLAG_DIST.
+ *   out_rgb  [n,h,w,3] uint8 or NULL: lab2rgb_transpose(L, out_ab)
+ *            (data/colorize_image.py:20-28,264).
+ * All pointers are DEVICE memory; asynchronous on `stream` (a cudaStream_t). */
+int idc_forward(idc_ctx* ctx, int n, int h, int w, const float* L_mc, const float* ab,
+                const float* mask, float maskcent, const float* glob, float* out_ab,
+                float* out_dist, uint8_t* out_rgb, void* stream);
+
+/* Same with HOST pointers (pinned staging inside; synchronous).  This is the call the
+ * reference-facing wrapper and bench.py's e2e leg use. */
+int idc_forward_host(idc_ctx* ctx, int n, int h, int w, const float* L_mc, const float* ab,
+                     const float* mask, float maskcent, const float* glob, float* out_ab,
+                     float* out_dist, uint8_t* out_rgb);
+
+/* Stand-alone post-process: lab2rgb_transpose (data/colorize_image.py:20-28).
+ * L [n,1,h,w] in [0,100] (NOT mean-centred), ab [n,2,h,w] -> rgb [n,h,w,3] uint8. DEVICE ptrs. */
+int idc_lab2rgb_u8(int device, int n, int h, int w, const float* L, const float* ab,
+                   uint8_t* rgb, void* stream);
+
+/* ---- introspection / test hooks (used by tests/, never by the product path) ---- */
+/* Copy a named activation ("conv1_2", "a8_1", ... see DESIGN.md) of the LAST forward to
+ * out [n,C,H,W] FP32 device memory; *c,*h,*w receive its shape. */
+int idc_get_activation(idc_ctx* ctx, const char* name, float* out_nchw, size_t out_floats,
+                       int* c, int* h, int* w);
+/* Overwrite a named activation from [n,C,H,W] FP32 device memory, then run ONE op by name. */
+int idc_set_activation(idc_ctx* ctx, const char* name, int n, const float* in_nchw);
+int idc_run_op(idc_ctx* ctx, const char* op_name, int n, void* stream);
+int idc_num_ops(idc_ctx* ctx);
+const char* idc_op_name(idc_ctx* ctx, int i);
+/* kernels launched by the last forward (gpu_launches in bench.py) */
+int idc_last_launch_count(idc_ctx* ctx);
+/* FLOPs (2*MACs, conv+deconv) of one image at the ctx geometry; includes model_class iff DIST */
+double idc_flops_per_image(idc_ctx* ctx);
+
+const char* idc_last_error(idc_ctx* ctx);
+int idc_destroy(idc_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDC_B200_H_ */

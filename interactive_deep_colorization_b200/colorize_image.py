@@ -1,0 +1,293 @@
+"""Host-side mirror of the reference wrapper classes, backed by the B200 engine.
+
+API kept verbatim from /root/reference/data/colorize_image.py so `ideepcolor.py:62-72`, the Qt
+GUI (`ui/gui_draw.py:109-113,258-286`) and the notebooks work unchanged:
+
+    ColorizeImageBase      (:39-198)   image prep, getters, full-res zoom
+    ColorizeImageB200      <-> ColorizeImageTorch      (:201-276)
+    ColorizeImageB200Dist  <-> ColorizeImageTorchDist  (:279-372)
+    ColorizeImageB200GlobDist <-> ColorizeImageCaffeGlobDist (:445-463) semantics on the torch scaling
+
+Differences, all deliberate: no matplotlib / scikit-image imports (colour math in .color);
+`prep_net` also accepts an in-memory `state_dict`; the network forward, the 529-bin softmax
+and the Lab->RGB post-process run in libidc_b200.so.  There is no CPU fallback.
+"""
+import numpy as np
+
+from . import color
+from .color import lab2rgb_transpose, rgb2lab_transpose  # noqa: F401  (re-exported like the reference)
+
+
+def put_point(input_ab, mask, loc, p, val):
+    """Notebook helper (DemoInteractiveColorization.ipynb:131-139): paint a (2p+1)^2 hint."""
+    input_ab[:, loc[0] - p:loc[0] + p + 1, loc[1] - p:loc[1] + p + 1] = np.array(val)[:, np.newaxis, np.newaxis]
+    mask[:, loc[0] - p:loc[0] + p + 1, loc[1] - p:loc[1] + p + 1] = 1
+    return (input_ab, mask)
+
+
+def _zoom(a, factors, order):
+    from scipy.ndimage import zoom
+    return zoom(a, factors, order=order)
+
+
+class ColorizeImageBase(object):
+    """Image state + getters.  Attribute and method names are the reference's public surface
+    (data/colorize_image.py:39-198); the bodies are organised around three helpers:
+    `_ingest` (RGB -> Lab planes), `_to_fullres` (scipy zoom to the full-resolution grid) and
+    `_render` (Lab planes -> uint8 RGB)."""
+
+    def __init__(self, Xd=256, Xfullres_max=10000):
+        self.Xd, self.Xfullres_max = Xd, Xfullres_max
+        self.img_l_set = self.net_set = self.img_just_set = False
+
+    def prep_net(self):
+        raise Exception("Should be implemented by base class")
+
+    # ----- image prep: reference load_image :52-66, set_image :68-77 -----
+    def _ingest(self, rgb_full, rgb_net):
+        self.img_rgb_fullres = rgb_full
+        self._set_img_lab_fullres_()
+        self.img_rgb = rgb_net
+        self._set_img_lab_()
+        self._set_img_lab_mc_()
+
+    def load_image(self, input_path):
+        import cv2
+        bgr = cv2.imread(input_path, 1)
+        if bgr is None:
+            raise IOError("cannot read image %r" % (input_path,))
+        full = cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB)
+        self._ingest(full.copy(), cv2.resize(full, (self.Xd, self.Xd)).copy())   # cv2 default = bilinear
+
+    def set_image(self, input_image):
+        self._ingest(input_image.copy(), input_image)
+
+    # ----- forward preconditions + hint normalisation: reference :79-96 -----
+    def net_forward(self, input_ab, input_mask):
+        for ok, what in ((self.img_l_set, 'an image'), (self.net_set, 'a net')):
+            if not ok:
+                print('I need to have %s!' % what)
+                return -1
+        self.input_ab, self.input_mask = input_ab, input_mask
+        self.input_ab_mc = (input_ab - self.ab_mean) / self.ab_norm
+        self.input_mask_mult = input_mask * self.mask_mult
+        return 0
+
+    def get_result_PSNR(self, result=-1, return_SE_map=False):
+        use_own = np.array((result)).flatten()[0] == -1
+        err2 = (1. * self.img_rgb - (self.get_img_forward() if use_own else result.copy())) ** 2
+        psnr = 20 * np.log10(255. / np.sqrt(np.mean(err2)))
+        return (psnr, err2) if return_SE_map else psnr
+
+    # ----- rendering helpers -----
+    @staticmethod
+    def _render(l_plane, ab_planes=None):
+        if ab_planes is None:
+            ab_planes = np.zeros((2,) + tuple(l_plane.shape[1:]))
+        return lab2rgb_transpose(l_plane, ab_planes)
+
+    def _to_fullres(self, planes, like, order):
+        fh = 1. * self.img_l_fullres.shape[1] / like.shape[1]
+        fw = 1. * self.img_l_fullres.shape[2] / like.shape[2]
+        return _zoom(planes, (1, fh, fw), order)
+
+    # ----- getters: reference :111-158 -----
+    def get_img_forward(self):
+        return self.output_rgb
+
+    def get_img_gray(self):
+        return self._render(self.img_l)
+
+    def get_img_gray_fullres(self):
+        return self._render(self.img_l_fullres)
+
+    def get_img_fullres(self):       # bilinear up-zoom of the (quantised) output ab, then Lab->RGB
+        return self._render(self.img_l_fullres, self._to_fullres(self.output_ab, self.output_ab, 1))
+
+    def get_input_img_fullres(self):
+        return self._render(self.img_l_fullres, self._to_fullres(self.input_ab, self.input_ab, 1))
+
+    def get_input_img(self):
+        return self._render(self.img_l, self.input_ab)
+
+    def get_img_mask(self):
+        return self._render(100. * (1 - self.input_mask))
+
+    def get_img_mask_fullres(self):
+        return self._render(100. * (1 - self._to_fullres(self.input_mask, self.input_ab, 0)))
+
+    def get_sup_img(self):
+        return self._render(50 * self.input_mask, self.input_ab)
+
+    def get_sup_fullres(self):
+        return self._render(50 * self._to_fullres(self.input_mask, self.output_ab, 0),
+                            self._to_fullres(self.input_ab, self.output_ab, 0))
+
+    # ----- Lab planes: reference :161-198 -----
+    @staticmethod
+    def _lab_planes(rgb):
+        lab = color.rgb2lab(rgb).transpose((2, 0, 1))
+        return lab, lab[[0]], lab[1:]
+
+    def _set_img_lab_fullres_(self):
+        big = max(self.img_rgb_fullres.shape[:2])
+        if big > self.Xfullres_max:          # cap the longest side
+            z = 1. * self.Xfullres_max / big
+            self.img_rgb_fullres = _zoom(self.img_rgb_fullres, (z, z, 1), 1)
+        self.img_lab_fullres, self.img_l_fullres, self.img_ab_fullres = self._lab_planes(self.img_rgb_fullres)
+
+    def _set_img_lab_(self):
+        self.img_lab, self.img_l, self.img_ab = self._lab_planes(self.img_rgb)
+
+    def _set_img_lab_mc_(self):
+        div = np.array((self.l_norm, self.ab_norm, self.ab_norm), dtype=np.float64).reshape(3, 1, 1)
+        sub = np.array((self.l_mean, self.ab_mean, self.ab_mean), dtype=np.float64).reshape(3, 1, 1) / div
+        self.img_lab_mc = self.img_lab / div - sub
+        self._set_img_l_()
+
+    def _set_img_l_(self):
+        self.img_l_mc = self.img_lab_mc[[0]]
+        self.img_l_set = True
+
+    def _set_img_ab_(self):
+        self.img_ab_mc = self.img_lab_mc[[1, 2]]
+
+    def _set_out_ab_(self):
+        # output_ab is re-derived from the uint8 RGB, i.e. quantised (reference :196-198)
+        self.output_lab = rgb2lab_transpose(self.output_rgb)
+        self.output_ab = self.output_lab[1:]
+
+
+class ColorizeImageB200(ColorizeImageBase):
+    """<-> ColorizeImageTorch (reference :201-276)."""
+
+    def __init__(self, Xd=256, maskcent=False, engine="tcgen05", fast_fp16=False):
+        print('ColorizeImageB200 instantiated')
+        ColorizeImageBase.__init__(self, Xd)
+        self.l_norm = 1.
+        self.ab_norm = 1.
+        self.l_mean = 50.
+        self.ab_mean = 0.
+        self.mask_mult = 1.
+        self.mask_cent = .5 if maskcent else 0
+        self.engine = engine
+        self.fast_fp16 = fast_fp16
+        # torch-path bin grid (reference :213; (b,a)-ordered meshgrid)
+        self.pts_in_hull = np.array(np.meshgrid(np.arange(-110, 120, 10), np.arange(-110, 120, 10))).reshape((2, 529)).T
+
+    def prep_net(self, gpu_id=None, path='', dist=False, state_dict=None):
+        import torch
+        from .model import SIGGRAPHGeneratorB200
+        print('path = %s' % path)
+        print('Model set! dist mode? ', dist)
+        self.net = SIGGRAPHGeneratorB200(dist=dist, device=0 if gpu_id is None else int(gpu_id), engine=self.engine,
+                                         fast_fp16=self.fast_fp16)
+        if state_dict is None:
+            state_dict = torch.load(path, map_location='cpu')
+        if hasattr(state_dict, '_metadata'):
+            del state_dict._metadata
+        self.net.load_state_dict(state_dict)
+        self.net.cuda()
+        self.net.eval()
+        self.net_set = True
+
+    def net_forward(self, input_ab, input_mask):
+        if ColorizeImageBase.net_forward(self, input_ab, input_mask) == -1:
+            return -1
+        A = np.ascontiguousarray(self.img_l_mc, dtype=np.float32)[None]
+        B = np.ascontiguousarray(self.input_ab_mc, dtype=np.float32)[None]
+        M = np.ascontiguousarray(self.input_mask_mult, dtype=np.float32)[None]
+        ctx = self.net._context(A.shape[-2], A.shape[-1], 1)
+        # one C-ABI call: H2D, forward, fused Lab->RGB post-process (reference :263-264), D2H
+        r = ctx.forward_host(A, B, M, float(self.mask_cent), want_dist=False, want_rgb=True)
+        self.output_ab_raw = r["ab"][0]          # raw net output (the parity quantity)
+        self.output_rgb = r["rgb"][0]
+        self._set_out_ab_()
+        return self.output_rgb
+
+    def get_img_forward(self):
+        return self.output_rgb
+
+    def get_img_gray(self):
+        return lab2rgb_transpose(self.img_l, np.zeros((2, self.Xd, self.Xd)))
+
+
+class _LazyUpsampledDist(object):
+    """[529, X, X] view of the [529, X/4, X/4] distribution: the reference materialises the
+    nearest x4 upsample (139 MB at 256^2, model.py:160); consumers only index it
+    (`dist_ab[:, h, w]`, data/colorize_image.py:329), so we replicate on read."""
+
+    def __init__(self, d64):
+        self.d64 = d64
+        self.shape = (d64.shape[0], d64.shape[1] * 4, d64.shape[2] * 4)
+        self.dtype = d64.dtype
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple) and len(idx) == 3 and all(isinstance(i, (int, np.integer)) for i in idx[1:]):
+            return self.d64[idx[0], idx[1] // 4, idx[2] // 4]
+        return self.__array__()[idx]
+
+    def __array__(self, dtype=None, copy=None):
+        a = np.repeat(np.repeat(self.d64, 4, axis=1), 4, axis=2)
+        return a.astype(dtype) if dtype is not None else a
+
+
+class ColorizeImageB200Dist(ColorizeImageB200):
+    """<-> ColorizeImageTorchDist (reference :279-372)."""
+
+    def __init__(self, Xd=256, maskcent=False, engine="tcgen05", fast_fp16=False, materialize_full=False):
+        ColorizeImageB200.__init__(self, Xd, engine=engine, fast_fp16=fast_fp16)
+        self.dist_ab_set = False
+        self.pts_grid = np.array(np.meshgrid(np.arange(-110, 120, 10), np.arange(-110, 120, 10))).reshape((2, 529)).T
+        self.in_hull = np.ones(529, dtype=bool)
+        self.AB = self.pts_grid.shape[0]
+        self.A = int(np.sqrt(self.AB))
+        self.B = int(np.sqrt(self.AB))
+        self.materialize_full = materialize_full
+        self.dist_entropy = np.zeros((self.Xd, self.Xd))
+        self.mask_cent = .5 if maskcent else 0
+
+    def prep_net(self, gpu_id=None, path='', dist=True, S=.2, state_dict=None):
+        ColorizeImageB200.prep_net(self, gpu_id=gpu_id, path=path, dist=dist, state_dict=state_dict)
+
+    def net_forward(self, input_ab, input_mask):
+        if ColorizeImageBase.net_forward(self, input_ab, input_mask) == -1:
+            return -1
+        A = np.ascontiguousarray(self.img_l_mc, dtype=np.float32)[None]
+        B = np.ascontiguousarray(self.input_ab_mc, dtype=np.float32)[None]
+        M = np.ascontiguousarray(self.input_mask_mult, dtype=np.float32)[None]
+        ctx = self.net._context(A.shape[-2], A.shape[-1], 1)
+        r = ctx.forward_host(A, B, M, float(self.mask_cent), want_dist=True)
+        self.output_ab_raw = r["ab"][0]
+        self.dist_ab_64 = r["dist"][0]                       # [529, X/4, X/4]
+        if self.materialize_full:
+            self.dist_ab = np.repeat(np.repeat(self.dist_ab_64, 4, axis=1), 4, axis=2)
+            self.dist_ab_full = np.zeros((self.AB, self.Xd, self.Xd))
+            self.dist_ab_full[self.in_hull, :, :] = self.dist_ab
+            self.dist_ab_grid = self.dist_ab_full.reshape((self.A, self.B, self.Xd, self.Xd))
+        else:
+            self.dist_ab = _LazyUpsampledDist(self.dist_ab_64)
+        self.dist_ab_set = True
+        # reference returns the regression output scaled by 110 twice (model.py:166-168, q1)
+        return self.output_ab_raw * 110.0
+
+    def get_ab_reccs(self, h, w, K=5, N=25000, return_conf=False):
+        """Colour suggestions at pixel (h, w) (reference :322-354): draw N samples from the
+        529-bin distribution by inverse-CDF lookup, k-means them, order clusters by mass."""
+        if not self.dist_ab_set:
+            print('Need to set prediction first')
+            return 0
+        from sklearn.cluster import KMeans
+        cdf = np.cumsum(np.asarray(self.dist_ab[:, h, w]))
+        cdf /= cdf[-1]
+        u = np.random.uniform(low=0, high=1.0, size=N)
+        samples = self.pts_in_hull[np.searchsorted(cdf, u, side='right'), :]   # == np.digitize(u, cdf)
+        km = KMeans(n_clusters=K).fit(samples)
+        mass = np.bincount(km.labels_, minlength=K)
+        order = np.argsort(mass)[::-1]
+        centers, conf = km.cluster_centers_[order, :], mass[order] / float(N)
+        return (centers, conf) if return_conf else centers
+
+    def compute_entropy(self):
+        d = np.asarray(self.dist_ab)
+        self.dist_entropy = np.sum(d * np.log(d), axis=0)

@@ -1,0 +1,734 @@
+// C ABI of libidc_b200.so (include/idc_b200.h): context, layer plan, weight packing, forward.
+// The plan restates the wiring of SIGGRAPHGenerator.forward
+// (/root/reference/models/pytorch/model.py:134-175) as a list of gather-GEMM ops; both engines
+// (idc_simt.cu FP32 CUDA cores, idc_umma.cu tcgen05) execute the same list.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "idc_internal.h"
+
+using namespace idc;
+
+struct idc_ctx : public idc::Ctx {};
+
+namespace {
+
+int fail(Ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CUDA_TRY(c, expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail(c, IDC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+constexpr float kBnEps = 1e-5f;  // nn.BatchNorm2d default
+
+int add_buf(Ctx* c, const char* name, int H, int W, int C) {
+  ActBuf b;
+  b.name = name; b.H = H; b.W = W; b.C = C;
+  c->bufs.push_back(b);
+  c->buf_index[name] = (int)c->bufs.size() - 1;
+  return (int)c->bufs.size() - 1;
+}
+
+// 3x3 conv (optionally dilated, optionally reading the ::2 decimation of its source)
+void add_conv(Ctx* c, const char* name, const char* wkey, const char* in, int s, int dil, const char* out, int act,
+              const char* bnkey, bool gadd = false) {
+  ConvOp op;
+  op.name = name; op.kind = OP_CONV; op.wkey[0] = wkey; op.bnkey = bnkey ? bnkey : "";
+  const ActBuf& ib = c->bufs[c->buf_index.at(in)];
+  const ActBuf& ob = c->bufs[c->buf_index.at(out)];
+  op.nsrc = 1;
+  op.src[0].buf = c->buf_index.at(in); op.src[0].s = s; op.src[0].cin = ib.C;
+  op.ncls = 1; op.ntaps = 9;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      Tap& t = op.taps[0][ky * 3 + kx];
+      t.src = 0; t.ky = ky; t.kx = kx; t.ty = s * (ky - 1) * dil; t.tx = s * (kx - 1) * dil;
+    }
+  op.Hl = ob.H; op.Wl = ob.W; op.out_buf = c->buf_index.at(out); op.os = 1;
+  op.cout = ob.C; op.cout_pad = ob.C; op.K = 9 * ib.C;
+  op.epi.act = act; op.epi.has_bn = bnkey != nullptr; op.epi.gadd = gadd;
+  op.flops_per_image = 2.0 * op.Hl * op.Wl * (double)op.cout * op.K;
+  c->ops.push_back(op);
+}
+
+// ConvTranspose2d(4x4, s2, p1) of `lo` + Conv2d(3x3) of the skip tensor, summed, then ReLU
+// (model.py:156-157,162-165: modelNup(x) + modelKshortN(skip), followed by modelN[0] = ReLU).
+void add_up(Ctx* c, const char* name, const char* dkey, const char* lo, const char* skey, const char* skip,
+            const char* out) {
+  ConvOp op;
+  op.name = name; op.kind = OP_UP; op.wkey[0] = dkey; op.wkey[1] = skey;
+  const ActBuf& lb = c->bufs[c->buf_index.at(lo)];
+  const ActBuf& sb = c->bufs[c->buf_index.at(skip)];
+  const ActBuf& ob = c->bufs[c->buf_index.at(out)];
+  op.nsrc = 2;
+  op.src[0].buf = c->buf_index.at(lo); op.src[0].s = 1; op.src[0].cin = lb.C;
+  op.src[1].buf = c->buf_index.at(skip); op.src[1].s = 2; op.src[1].cin = sb.C;
+  op.ncls = 4; op.ntaps = 13;
+  for (int cls = 0; cls < 4; ++cls) {
+    const int py = cls >> 1, px = cls & 1;
+    // oy = 2*iy - 1 + ky  =>  parity 0: (ky=1, iy=y), (ky=3, iy=y-1); parity 1: (ky=0, iy=y+1), (ky=2, iy=y)
+    const int kys[2][2] = {{1, 3}, {0, 2}};
+    const int tys[2][2] = {{0, -1}, {1, 0}};
+    int t = 0;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        Tap& tp = op.taps[cls][t++];
+        tp.src = 0; tp.ky = kys[py][a]; tp.kx = kys[px][b]; tp.ty = tys[py][a]; tp.tx = tys[px][b];
+      }
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        Tap& tp = op.taps[cls][t++];
+        tp.src = 1; tp.ky = ky; tp.kx = kx; tp.ty = py + ky - 1; tp.tx = px + kx - 1;
+      }
+  }
+  op.Hl = lb.H; op.Wl = lb.W; op.out_buf = c->buf_index.at(out); op.os = 2;
+  op.cout = ob.C; op.cout_pad = ob.C; op.K = 4 * lb.C + 9 * sb.C;
+  op.epi.act = ACT_RELU;
+  op.flops_per_image = 2.0 * 4 * op.Hl * op.Wl * (double)op.cout * op.K;
+  c->ops.push_back(op);
+}
+
+void build_plan(Ctx* c) {
+  const int H = c->H, W = c->W;
+  add_buf(c, "a1_1", H, W, 64); add_buf(c, "conv1_2", H, W, 64);
+  add_buf(c, "a2_1", H / 2, W / 2, 128); add_buf(c, "conv2_2", H / 2, W / 2, 128);
+  add_buf(c, "a3_1", H / 4, W / 4, 256); add_buf(c, "a3_2", H / 4, W / 4, 256); add_buf(c, "conv3_3", H / 4, W / 4, 256);
+  const char* n8[] = {"a4_1", "a4_2", "conv4_3", "a5_1", "a5_2", "conv5_3", "a6_1", "a6_2", "conv6_3",
+                      "a7_1", "a7_2", "conv7_3"};
+  for (const char* nm : n8) add_buf(c, nm, H / 8, W / 8, 512);
+  add_buf(c, "a8_1", H / 4, W / 4, 256); add_buf(c, "a8_2", H / 4, W / 4, 256); add_buf(c, "conv8_3", H / 4, W / 4, 256);
+  add_buf(c, "a9_1", H / 2, W / 2, 128); add_buf(c, "conv9_3", H / 2, W / 2, 128);
+  add_buf(c, "a10_1", H, W, 128);
+  const bool keep10 = c->simt || (c->flags & IDC_FLAG_KEEP_CONV10);
+  if (keep10) add_buf(c, "conv10_2", H, W, 128);
+
+  // model1 (conv1_1 is the fused pack+conv kernel in idc_heads.cu)            model.py:13-17
+  add_conv(c, "c1_2", "model1.2", "a1_1", 1, 1, "conv1_2", ACT_RELU, "model1.4");
+  // model2 on conv1_2[:, :, ::2, ::2]                                        model.py:149, 21-25
+  add_conv(c, "c2_1", "model2.0", "conv1_2", 2, 1, "a2_1", ACT_RELU, nullptr);
+  add_conv(c, "c2_2", "model2.2", "a2_1", 1, 1, "conv2_2", ACT_RELU, "model2.4");
+  // model3                                                                   model.py:150, 29-35
+  add_conv(c, "c3_1", "model3.0", "conv2_2", 2, 1, "a3_1", ACT_RELU, nullptr);
+  add_conv(c, "c3_2", "model3.2", "a3_1", 1, 1, "a3_2", ACT_RELU, nullptr);
+  add_conv(c, "c3_3", "model3.4", "a3_2", 1, 1, "conv3_3", ACT_RELU, "model3.6");
+  // model4 (+ global-hints vector added to conv4_3norm, deploy_nodist.prototxt:501-527)  model.py:151, 39-45
+  add_conv(c, "c4_1", "model4.0", "conv3_3", 2, 1, "a4_1", ACT_RELU, nullptr);
+  add_conv(c, "c4_2", "model4.2", "a4_1", 1, 1, "a4_2", ACT_RELU, nullptr);
+  add_conv(c, "c4_3", "model4.4", "a4_2", 1, 1, "conv4_3", ACT_RELU, "model4.6", c->glob);
+  // model5, model6 (dilation 2), model7                                       model.py:48-72
+  add_conv(c, "c5_1", "model5.0", "conv4_3", 1, 2, "a5_1", ACT_RELU, nullptr);
+  add_conv(c, "c5_2", "model5.2", "a5_1", 1, 2, "a5_2", ACT_RELU, nullptr);
+  add_conv(c, "c5_3", "model5.4", "a5_2", 1, 2, "conv5_3", ACT_RELU, "model5.6");
+  add_conv(c, "c6_1", "model6.0", "conv5_3", 1, 2, "a6_1", ACT_RELU, nullptr);
+  add_conv(c, "c6_2", "model6.2", "a6_1", 1, 2, "a6_2", ACT_RELU, nullptr);
+  add_conv(c, "c6_3", "model6.4", "a6_2", 1, 2, "conv6_3", ACT_RELU, "model6.6");
+  add_conv(c, "c7_1", "model7.0", "conv6_3", 1, 1, "a7_1", ACT_RELU, nullptr);
+  add_conv(c, "c7_2", "model7.2", "a7_1", 1, 1, "a7_2", ACT_RELU, nullptr);
+  add_conv(c, "c7_3", "model7.4", "a7_2", 1, 1, "conv7_3", ACT_RELU, "model7.6");
+  // decoder level 8                                                          model.py:156-157, 75-83
+  add_up(c, "up8", "model8up.0", "conv7_3", "model3short8.0", "conv3_3", "a8_1");
+  add_conv(c, "c8_2", "model8.1", "a8_1", 1, 1, "a8_2", ACT_RELU, nullptr);
+  add_conv(c, "c8_3", "model8.3", "a8_2", 1, 1, "conv8_3", ACT_RELU, "model8.5");
+  // class head on conv8_3 (dist only)                                        model.py:105, 160
+  if (c->dist) {
+    ConvOp op;
+    op.name = "class"; op.kind = OP_CLASS; op.wkey[0] = "model_class.0";
+    const ActBuf& ib = c->bufs[c->buf_index.at("conv8_3")];
+    op.nsrc = 1; op.src[0].buf = c->buf_index.at("conv8_3"); op.src[0].s = 1; op.src[0].cin = ib.C;
+    op.ncls = 1; op.ntaps = 1;
+    op.taps[0][0] = Tap{0, 0, 0, 0, 0};
+    op.Hl = ib.H; op.Wl = ib.W; op.out_buf = -1; op.os = 1;
+    op.cout = 529; op.cout_pad = 576; op.K = ib.C; op.out_f32 = true;
+    op.flops_per_image = 2.0 * op.Hl * op.Wl * 529.0 * op.K;
+    c->ops.push_back(op);
+  }
+  // level 9                                                                  model.py:162-163, 86-93
+  add_up(c, "up9", "model9up.0", "conv8_3", "model2short9.0", "conv2_2", "a9_1");
+  add_conv(c, "c9_2", "model9.1", "a9_1", 1, 1, "conv9_3", ACT_RELU, "model9.3");
+  // level 10                                                                 model.py:164-165, 96-102
+  add_up(c, "up10", "model10up.0", "conv9_3", "model1short10.0", "conv1_2", "a10_1");
+  if (keep10) {
+    add_conv(c, "c10_2", "model10.1", "a10_1", 1, 1, "conv10_2", ACT_LEAKY02, nullptr);
+  } else {
+    // conv10_2 never leaves the SM: model_out (1x1 128->2, tanh, x110) runs in the epilogue
+    add_buf(c, "conv10_2_virtual", 0, 0, 128);
+    ConvOp op;
+    op.name = "c10_2"; op.kind = OP_CONV; op.wkey[0] = "model10.1";
+    const ActBuf& ib = c->bufs[c->buf_index.at("a10_1")];
+    op.nsrc = 1; op.src[0].buf = c->buf_index.at("a10_1"); op.src[0].s = 1; op.src[0].cin = ib.C;
+    op.ncls = 1; op.ntaps = 9;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) op.taps[0][ky * 3 + kx] = Tap{0, ky, kx, ky - 1, kx - 1};
+    op.Hl = ib.H; op.Wl = ib.W; op.out_buf = -1; op.os = 1;
+    op.cout = 128; op.cout_pad = 128; op.K = 9 * ib.C;
+    op.epi.act = ACT_LEAKY02; op.fuse_out_head = true;
+    op.flops_per_image = 2.0 * op.Hl * op.Wl * 128.0 * op.K;
+    c->ops.push_back(op);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight arena
+// ---------------------------------------------------------------------------------------------
+struct ArenaLayout {
+  size_t off = 0;
+  template <typename T>
+  size_t take(size_t count) {
+    off = (off + 255) & ~size_t(255);
+    size_t o = off;
+    off += count * sizeof(T);
+    return o;
+  }
+};
+
+const char* kGlobKeys[4] = {"glob.0", "glob.1", "glob.2", "glob.3"};
+
+// Assigns arena offsets to every packed tensor (deterministic: same on every rank).
+size_t layout_arena(Ctx* c, char* base) {
+  ArenaLayout L;
+  auto P = [&](size_t o) { return base ? base + o : nullptr; };
+  c->w11 = (float*)P(L.take<float>(36 * 64));
+  c->b11 = (float*)P(L.take<float>(64));
+  c->wout = (float*)P(L.take<float>(256));
+  c->bout = (float*)P(L.take<float>(4));
+  for (auto& op : c->ops) {
+    op.epi.bias = (float*)P(L.take<float>(op.cout_pad));
+    op.epi.scale = (float*)P(L.take<float>(op.cout_pad));
+    op.epi.shift = (float*)P(L.take<float>(op.cout_pad));
+    const size_t nw = (size_t)op.ncls * op.K * op.cout_pad;
+    if (c->simt) {
+      op.w_simt = (float*)P(L.take<float>(nw));
+    } else {
+      op.w_hi = (__half*)P(L.take<__half>(nw));
+      op.w_lo = (__half*)P(L.take<__half>(nw));
+    }
+  }
+  if (c->glob) {
+    for (int l = 0; l < 4; ++l) {
+      const int cin = l == 0 ? 316 : 512;
+      c->gw[l] = (float*)P(L.take<float>((size_t)512 * cin));
+      c->gb[l] = (float*)P(L.take<float>(512));
+      c->gscale[l] = (float*)P(L.take<float>(512));
+      c->gshift[l] = (float*)P(L.take<float>(512));
+    }
+  }
+  return (L.off + 255) & ~size_t(255);
+}
+
+const HostTensor* find(Ctx* c, const std::string& key) {
+  auto it = c->raw.find(key);
+  return it == c->raw.end() ? nullptr : &it->second;
+}
+
+bool check_dims(const HostTensor* t, std::initializer_list<int64_t> d) {
+  if (!t || t->dims.size() != d.size()) return false;
+  size_t i = 0;
+  for (int64_t v : d)
+    if (t->dims[i++] != v) return false;
+  return true;
+}
+
+void split_f16(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+// BN(eval) -> y = x*scale + shift   (model.py:17.. ; F.batch_norm with running stats)
+void fold_bn(const HostTensor& g, const HostTensor& b, const HostTensor& m, const HostTensor& v, int C, float* scale,
+             float* shift) {
+  for (int i = 0; i < C; ++i) {
+    const double s = (double)g.data[i] / sqrt((double)v.data[i] + (double)kBnEps);
+    scale[i] = (float)s;
+    shift[i] = (float)((double)b.data[i] - (double)m.data[i] * s);
+  }
+}
+
+int pack_weights(Ctx* c, char* host) {
+  // translate device pointers (already laid out relative to c->arena) to host staging pointers
+  auto H = [&](void* dev) { return host + ((char*)dev - c->arena); };
+  // conv1_1: [36][64], k = (ky*3+kx)*4 + cin                                       model.py:13
+  {
+    const HostTensor* w = find(c, "model1.0.weight");
+    const HostTensor* b = find(c, "model1.0.bias");
+    if (!check_dims(w, {64, 4, 3, 3}) || !check_dims(b, {64})) return fail(c, IDC_ERR_KEY, "missing/bad model1.0.*");
+    float* dst = (float*)H(c->w11);
+    for (int co = 0; co < 64; ++co)
+      for (int ci = 0; ci < 4; ++ci)
+        for (int t = 0; t < 9; ++t) dst[(t * 4 + ci) * 64 + co] = w->data[((size_t)co * 4 + ci) * 9 + t];
+    memcpy(H(c->b11), b->data.data(), 64 * sizeof(float));
+  }
+  {
+    const HostTensor* w = find(c, "model_out.0.weight");
+    const HostTensor* b = find(c, "model_out.0.bias");
+    if (!check_dims(w, {2, 128, 1, 1}) || !check_dims(b, {2})) return fail(c, IDC_ERR_KEY, "missing/bad model_out.0.*");
+    memcpy(H(c->wout), w->data.data(), 256 * sizeof(float));
+    float* bo = (float*)H(c->bout);
+    bo[0] = b->data[0]; bo[1] = b->data[1]; bo[2] = bo[3] = 0.f;
+  }
+  for (auto& op : c->ops) {
+    float* bias = (float*)H(op.epi.bias);
+    float* scale = (float*)H(op.epi.scale);
+    float* shift = (float*)H(op.epi.shift);
+    for (int i = 0; i < op.cout_pad; ++i) { bias[i] = 0.f; scale[i] = 1.f; shift[i] = 0.f; }
+    const HostTensor* w[2] = {nullptr, nullptr};
+    for (int s = 0; s < op.nsrc; ++s) {
+      w[s] = find(c, op.wkey[s] + ".weight");
+      const HostTensor* b = find(c, op.wkey[s] + ".bias");
+      const int cin = op.src[s].cin;
+      bool ok;
+      if (op.kind == OP_UP && s == 0) ok = check_dims(w[s], {cin, op.cout, 4, 4});
+      else if (op.kind == OP_CLASS) ok = check_dims(w[s], {op.cout, cin, 1, 1});
+      else ok = check_dims(w[s], {op.cout, cin, 3, 3});
+      if (!ok || !check_dims(b, {op.cout})) return fail(c, IDC_ERR_KEY, "missing/bad %s.*", op.wkey[s].c_str());
+      for (int i = 0; i < op.cout; ++i) bias[i] += b->data[i];
+    }
+    if (op.epi.has_bn) {
+      const HostTensor* g = find(c, op.bnkey + ".weight");
+      const HostTensor* b = find(c, op.bnkey + ".bias");
+      const HostTensor* m = find(c, op.bnkey + ".running_mean");
+      const HostTensor* v = find(c, op.bnkey + ".running_var");
+      if (!check_dims(g, {op.cout}) || !check_dims(b, {op.cout}) || !check_dims(m, {op.cout}) ||
+          !check_dims(v, {op.cout}))
+        return fail(c, IDC_ERR_KEY, "missing/bad %s.*", op.bnkey.c_str());
+      fold_bn(*g, *b, *m, *v, op.cout, scale, shift);
+    }
+    // weight value of (class, tap, ci, co)
+    auto wval = [&](int cls, int t, int ci, int co) -> float {
+      const Tap& tp = op.taps[cls][t];
+      const HostTensor* ww = w[tp.src];
+      const int cin = op.src[tp.src].cin;
+      if (op.kind == OP_UP && tp.src == 0)  // ConvTranspose2d weight is [Cin][Cout][4][4]
+        return ww->data[(((size_t)ci * op.cout + co) * 4 + tp.ky) * 4 + tp.kx];
+      if (op.kind == OP_CLASS) return ww->data[(size_t)co * cin + ci];
+      return ww->data[(((size_t)co * cin + ci) * 3 + tp.ky) * 3 + tp.kx];
+    };
+    if (c->simt) {
+      float* dst = (float*)H(op.w_simt);
+      memset(dst, 0, sizeof(float) * (size_t)op.ncls * op.K * op.cout_pad);
+      for (int cls = 0; cls < op.ncls; ++cls) {
+        int k0 = 0;
+        for (int t = 0; t < op.ntaps; ++t) {
+          const int cin = op.src[op.taps[cls][t].src].cin;
+          for (int ci = 0; ci < cin; ++ci)
+            for (int co = 0; co < op.cout; ++co)
+              dst[((size_t)cls * op.K + k0 + ci) * op.cout_pad + co] = wval(cls, t, ci, co);
+          k0 += cin;
+        }
+      }
+    } else {
+      // K-major FP16 hi/lo rows, one row per (class, cout); per-output-channel power-of-two scale so
+      // the lo term stays in FP16's normal range; the epilogue multiplies by 1/scale (exact).
+      __half* hi = (__half*)H(op.w_hi);
+      __half* lo = (__half*)H(op.w_lo);
+      memset(hi, 0, sizeof(__half) * (size_t)op.ncls * op.K * op.cout_pad);
+      memset(lo, 0, sizeof(__half) * (size_t)op.ncls * op.K * op.cout_pad);
+      for (int co = 0; co < op.cout; ++co) {
+        float mx = 0.f;
+        for (int cls = 0; cls < op.ncls; ++cls)
+          for (int t = 0; t < op.ntaps; ++t) {
+            const int cin = op.src[op.taps[cls][t].src].cin;
+            for (int ci = 0; ci < cin; ++ci) mx = fmaxf(mx, fabsf(wval(cls, t, ci, co)));
+          }
+        int e = 0;
+        if (mx > 0.f) {
+          frexpf(mx, &e);       // mx = f * 2^e, f in [0.5, 1)
+          e = 9 - e;            // scaled max in [256, 512)
+          e = std::max(-24, std::min(24, e));
+        }
+        const float sc = ldexpf(1.f, e);
+        bias[co] *= sc;                 // exact (power of two)
+        scale[co] *= ldexpf(1.f, -e);
+        for (int cls = 0; cls < op.ncls; ++cls) {
+          int k0 = 0;
+          for (int t = 0; t < op.ntaps; ++t) {
+            const int cin = op.src[op.taps[cls][t].src].cin;
+            for (int ci = 0; ci < cin; ++ci) {
+              const size_t idx = ((size_t)cls * op.cout_pad + co) * op.K + k0 + ci;
+              split_f16(wval(cls, t, ci, co) * sc, hi[idx], lo[idx]);
+            }
+            k0 += cin;
+          }
+        }
+      }
+    }
+  }
+  if (c->glob) {
+    for (int l = 0; l < 4; ++l) {
+      const int cin = l == 0 ? 316 : 512;
+      const std::string k = kGlobKeys[l];
+      const HostTensor* w = find(c, k + ".weight");
+      const HostTensor* b = find(c, k + ".bias");
+      const HostTensor* g = find(c, k + ".bn.weight");
+      const HostTensor* bb = find(c, k + ".bn.bias");
+      const HostTensor* m = find(c, k + ".bn.running_mean");
+      const HostTensor* v = find(c, k + ".bn.running_var");
+      if (!check_dims(w, {512, cin}) || !check_dims(b, {512}) || !check_dims(g, {512}) || !check_dims(bb, {512}) ||
+          !check_dims(m, {512}) || !check_dims(v, {512}))
+        return fail(c, IDC_ERR_KEY, "missing/bad %s.* (global hints)", k.c_str());
+      memcpy(H(c->gw[l]), w->data.data(), sizeof(float) * 512 * cin);
+      memcpy(H(c->gb[l]), b->data.data(), sizeof(float) * 512);
+      fold_bn(*g, *bb, *m, *v, 512, (float*)H(c->gscale[l]), (float*)H(c->gshift[l]));
+    }
+  }
+  return IDC_OK;
+}
+
+int alloc_workspace(Ctx* c) {
+  for (auto& b : c->bufs) {
+    if (b.H == 0) continue;
+    const size_t elems = (size_t)c->max_n * b.H * b.W * b.C;
+    if (c->simt) {
+      CUDA_TRY(c, cudaMalloc(&b.p0, elems * sizeof(float)));
+    } else {
+      CUDA_TRY(c, cudaMalloc(&b.p0, elems * sizeof(__half)));
+      if (!c->fast) CUDA_TRY(c, cudaMalloc(&b.p1, elems * sizeof(__half)));
+    }
+  }
+  if (c->dist) CUDA_TRY(c, cudaMalloc(&c->logits, sizeof(float) * (size_t)c->max_n * (c->H / 4) * (c->W / 4) * 576));
+  if (c->glob) {
+    CUDA_TRY(c, cudaMalloc(&c->gvec, sizeof(float) * (size_t)c->max_n * 512));
+    CUDA_TRY(c, cudaMalloc(&c->gtmp, sizeof(float) * (size_t)2 * c->max_n * 512));
+  }
+  CUDA_TRY(c, cudaHostAlloc(&c->h_err, 64, cudaHostAllocMapped));
+  memset(c->h_err, 0, 64);
+  CUDA_TRY(c, cudaHostGetDevicePointer(&c->d_err, c->h_err, 0));
+  return IDC_OK;
+}
+
+int plan_engines(Ctx* c) {
+  if (c->simt) return IDC_OK;
+  for (auto& op : c->ops) {
+    int rc = umma_plan_op(c, op);
+    if (rc != IDC_OK) return rc;
+  }
+  return IDC_OK;
+}
+
+int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mask, float maskcent, const float* glob,
+                float* out_ab, float* out_dist, uint8_t* out_rgb, cudaStream_t st) {
+  c->launch_count = 0;
+  c->gadd_active = false;
+  if (glob && c->glob) {
+    CUDA_TRY(c, launch_global_mlp(c, n, glob, st));
+    c->gadd_active = true;
+  }
+  CUDA_TRY(c, launch_conv1_1(c, n, L, ab, mask, maskcent, st));
+  for (auto& op : c->ops) {
+    if (c->simt) CUDA_TRY(c, simt_run_op(c, op, n, st));
+    else CUDA_TRY(c, umma_run_op(c, op, n, op.fuse_out_head ? out_ab : nullptr, 1.0f, st));
+  }
+  const bool fused = !c->simt && !(c->flags & IDC_FLAG_KEEP_CONV10);
+  if (!fused) CUDA_TRY(c, launch_out_head(c, n, out_ab, st));
+  if (out_dist) CUDA_TRY(c, launch_softmax529(c, n, out_dist, st));
+  if (out_rgb) {
+    CUDA_TRY(c, launch_lab2rgb(n, c->H, c->W, L, 50.0f, out_ab, out_rgb, st));
+    c->launch_count++;
+  }
+  c->last_n = n;
+  return IDC_OK;
+}
+
+int check_forward_args(Ctx* c, int n, int h, int w, const void* L, const void* ab, const void* mask, const void* glob,
+                       const void* out_ab, const void* out_dist) {
+  if (!c->weights_ready) return fail(c, IDC_ERR_STATE, "idc_forward before idc_finalize_weights");
+  if (n < 1 || n > c->max_n) return fail(c, IDC_ERR_ARG, "n=%d outside [1,%d]", n, c->max_n);
+  if (h != c->H || w != c->W) return fail(c, IDC_ERR_ARG, "geometry %dx%d != ctx geometry %dx%d", h, w, c->H, c->W);
+  if (!L || !ab || !mask || !out_ab) return fail(c, IDC_ERR_ARG, "null L/ab/mask/out_ab");
+  if (out_dist && !c->dist) return fail(c, IDC_ERR_ARG, "out_dist requires IDC_FLAG_DIST");
+  if (glob && !c->glob) return fail(c, IDC_ERR_ARG, "glob requires IDC_FLAG_GLOBAL_HINTS");
+  return IDC_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* idc_version(void) { return "idc_b200 0.1 sm_100a (tcgen05 split-fp16 + fp32 simt engines)"; }
+
+int idc_create(int device, int max_n, int h, int w, unsigned flags, idc_ctx** out) {
+  if (!out) return IDC_ERR_ARG;
+  *out = nullptr;
+  if (max_n < 1 || h < 8 || w < 8 || (h % 8) || (w % 8)) return IDC_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return IDC_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return IDC_ERR_CUDA;
+  if (prop.major != 10) return IDC_ERR_UNSUPPORTED;  // sm_100a cubins only; no fallback
+  if (cudaSetDevice(device) != cudaSuccess) return IDC_ERR_CUDA;
+  idc_ctx* c = new idc_ctx();
+  c->dev = device; c->max_n = max_n; c->H = h; c->W = w; c->flags = flags;
+  c->simt = flags & IDC_FLAG_ENGINE_SIMT;
+  c->fast = (flags & IDC_FLAG_FAST_FP16) && !c->simt;
+  c->dist = flags & IDC_FLAG_DIST;
+  c->glob = flags & IDC_FLAG_GLOBAL_HINTS;
+  build_plan(c);
+  int rc = alloc_workspace(c);
+  if (rc != IDC_OK) {
+    fprintf(stderr, "idc_create: %s\n", c->err.c_str());
+    idc_destroy(c);
+    return rc;
+  }
+  cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+  *out = c;
+  return IDC_OK;
+}
+
+int idc_load_tensor(idc_ctx* c, const char* key, const void* data, int dtype, int ndim, const int64_t* dims) {
+  if (!c || !key || !data || ndim < 0 || ndim > 8 || (ndim && !dims)) return fail(c, IDC_ERR_ARG, "bad load_tensor args");
+  HostTensor t;
+  size_t count = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (dims[i] < 0) return fail(c, IDC_ERR_ARG, "negative dim");
+    t.dims.push_back(dims[i]);
+    count *= (size_t)dims[i];
+  }
+  t.data.resize(count);
+  switch (dtype) {
+    case IDC_F32: memcpy(t.data.data(), data, count * sizeof(float)); break;
+    case IDC_F64: for (size_t i = 0; i < count; ++i) t.data[i] = (float)((const double*)data)[i]; break;
+    case IDC_I64: for (size_t i = 0; i < count; ++i) t.data[i] = (float)((const int64_t*)data)[i]; break;
+    default: return fail(c, IDC_ERR_ARG, "unknown dtype %d", dtype);
+  }
+  c->raw[key] = std::move(t);
+  c->weights_ready = false;
+  return IDC_OK;
+}
+
+int idc_reserve_weights(idc_ctx* c) {
+  if (!c) return IDC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  if (!c->arena) {
+    c->arena_bytes = layout_arena(c, nullptr);
+    CUDA_TRY(c, cudaMalloc(&c->arena, c->arena_bytes));
+    layout_arena(c, c->arena);
+  }
+  return IDC_OK;
+}
+
+int idc_finalize_weights(idc_ctx* c) {
+  if (!c) return IDC_ERR_ARG;
+  int rc = idc_reserve_weights(c);
+  if (rc != IDC_OK) return rc;
+  std::vector<char> host(c->arena_bytes, 0);
+  rc = pack_weights(c, host.data());
+  if (rc != IDC_OK) return rc;
+  CUDA_TRY(c, cudaMemcpy(c->arena, host.data(), c->arena_bytes, cudaMemcpyHostToDevice));
+  return idc_adopt_weights(c);
+}
+
+int idc_adopt_weights(idc_ctx* c) {
+  if (!c || !c->arena) return fail(c, IDC_ERR_STATE, "no arena");
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  int rc = plan_engines(c);
+  if (rc != IDC_OK) return rc;
+  c->raw.clear();
+  c->weights_ready = true;
+  if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+  return IDC_OK;
+}
+
+int idc_weights_arena(idc_ctx* c, void** dev_ptr, size_t* bytes) {
+  if (!c || !dev_ptr || !bytes) return IDC_ERR_ARG;
+  if (!c->arena) return fail(c, IDC_ERR_STATE, "arena not allocated");
+  *dev_ptr = c->arena; *bytes = c->arena_bytes;
+  return IDC_OK;
+}
+
+int idc_forward(idc_ctx* c, int n, int h, int w, const float* L, const float* ab, const float* mask, float maskcent,
+                const float* glob, float* out_ab, float* out_dist, uint8_t* out_rgb, void* stream) {
+  if (!c) return IDC_ERR_ARG;
+  int rc = check_forward_args(c, n, h, w, L, ab, mask, glob, out_ab, out_dist);
+  if (rc != IDC_OK) return rc;
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  return run_forward(c, n, L, ab, mask, maskcent, glob, out_ab, out_dist, out_rgb, (cudaStream_t)stream);
+}
+
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+int idc_forward_host(idc_ctx* c, int n, int h, int w, const float* L, const float* ab, const float* mask,
+                     float maskcent, const float* glob, float* out_ab, float* out_dist, uint8_t* out_rgb) {
+  if (!c) return IDC_ERR_ARG;
+  int rc = check_forward_args(c, n, h, w, L, ab, mask, glob, out_ab, out_dist);
+  if (rc != IDC_OK) return rc;
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  const size_t HW = (size_t)c->H * c->W, HW4 = (size_t)(c->H / 4) * (c->W / 4);
+  if (!c->d_in) {
+    c->in_floats = (size_t)c->max_n * (4 * HW + 316);
+    c->out_floats = (size_t)c->max_n * (2 * HW + (c->dist ? 529 * HW4 : 0));
+    CUDA_TRY(c, cudaMalloc(&c->d_in, c->in_floats * sizeof(float)));
+    CUDA_TRY(c, cudaMalloc(&c->d_out, c->out_floats * sizeof(float)));
+    CUDA_TRY(c, cudaMalloc(&c->d_rgb, (size_t)c->max_n * HW * 3));
+    CUDA_TRY(c, cudaMallocHost(&c->h_in, c->in_floats * sizeof(float)));
+    CUDA_TRY(c, cudaMallocHost(&c->h_out, c->out_floats * sizeof(float)));
+    CUDA_TRY(c, cudaMallocHost(&c->h_rgb, (size_t)c->max_n * HW * 3));
+  }
+  cudaStream_t st = c->own_stream;
+  // device-side layout of the staging block: [L | ab | mask | glob], [out_ab | out_dist]
+  float* dL = c->d_in; float* dab = dL + (size_t)c->max_n * HW; float* dmask = dab + (size_t)c->max_n * 2 * HW;
+  float* dglob = dmask + (size_t)c->max_n * HW;
+  float* dout = c->d_out; float* ddist = dout + (size_t)c->max_n * 2 * HW;
+  auto h2d = [&](float* d, const float* src, size_t count, size_t stage_off) -> cudaError_t {
+    const float* s = src;
+    if (!is_pinned(src)) {   // pageable caller memory: stage through our pinned block
+      memcpy(c->h_in + stage_off, src, count * sizeof(float));
+      s = c->h_in + stage_off;
+    }
+    return cudaMemcpyAsync(d, s, count * sizeof(float), cudaMemcpyHostToDevice, st);
+  };
+  CUDA_TRY(c, h2d(dL, L, n * HW, 0));
+  CUDA_TRY(c, h2d(dab, ab, n * 2 * HW, (size_t)c->max_n * HW));
+  CUDA_TRY(c, h2d(dmask, mask, n * HW, (size_t)c->max_n * 3 * HW));
+  if (glob) CUDA_TRY(c, h2d(dglob, glob, (size_t)n * 316, (size_t)c->max_n * 4 * HW));
+
+  const bool use_graph = !(c->flags & IDC_FLAG_NO_GRAPH) && n <= 4;
+  const bool want_dist = out_dist != nullptr, want_rgb = out_rgb != nullptr, want_glob = glob != nullptr;
+  if (use_graph) {
+    const void* key[8] = {(void*)(size_t)n, (void*)(size_t)want_dist, (void*)(size_t)want_rgb, (void*)(size_t)want_glob,
+                          nullptr, nullptr, nullptr, nullptr};
+    if (!c->graph_exec || memcmp(key, c->graph_ptrs, sizeof(key)) != 0 || c->graph_maskcent != maskcent) {
+      if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+      cudaGraph_t g = nullptr;
+      CUDA_TRY(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      rc = run_forward(c, n, dL, dab, dmask, maskcent, want_glob ? dglob : nullptr, dout, want_dist ? ddist : nullptr,
+                       want_rgb ? c->d_rgb : nullptr, st);
+      cudaError_t ce = cudaStreamEndCapture(st, &g);
+      if (rc != IDC_OK) { if (g) cudaGraphDestroy(g); return rc; }
+      CUDA_TRY(c, ce);
+      CUDA_TRY(c, cudaGraphInstantiate(&c->graph_exec, g, 0));
+      cudaGraphDestroy(g);
+      memcpy(c->graph_ptrs, key, sizeof(key));
+      c->graph_maskcent = maskcent;
+      c->graph_launches = c->launch_count;
+    }
+    CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, st));
+    c->launch_count = c->graph_launches;
+  } else {
+    rc = run_forward(c, n, dL, dab, dmask, maskcent, want_glob ? dglob : nullptr, dout, want_dist ? ddist : nullptr,
+                     want_rgb ? c->d_rgb : nullptr, st);
+    if (rc != IDC_OK) return rc;
+  }
+  auto d2h = [&](void* dst, const void* d, size_t bytes, void* stage) -> cudaError_t {
+    if (is_pinned(dst)) return cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, st);
+    return cudaMemcpyAsync(stage, d, bytes, cudaMemcpyDeviceToHost, st);
+  };
+  CUDA_TRY(c, d2h(out_ab, dout, n * 2 * HW * sizeof(float), c->h_out));
+  if (want_dist) CUDA_TRY(c, d2h(out_dist, ddist, n * 529 * HW4 * sizeof(float), c->h_out + (size_t)c->max_n * 2 * HW));
+  if (want_rgb) CUDA_TRY(c, d2h(out_rgb, c->d_rgb, n * HW * 3, c->h_rgb));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  if (!is_pinned(out_ab)) memcpy(out_ab, c->h_out, n * 2 * HW * sizeof(float));
+  if (want_dist && !is_pinned(out_dist)) memcpy(out_dist, c->h_out + (size_t)c->max_n * 2 * HW, n * 529 * HW4 * sizeof(float));
+  if (want_rgb && !is_pinned(out_rgb)) memcpy(out_rgb, c->h_rgb, n * HW * 3);
+  const int werr = *(volatile int*)c->h_err;
+  if (werr) return fail(c, IDC_ERR_WATCHDOG, "device pipeline watchdog fired (code %d)", werr);
+  return IDC_OK;
+}
+
+int idc_lab2rgb_u8(int device, int n, int h, int w, const float* L, const float* ab, uint8_t* rgb, void* stream) {
+  if (n < 1 || h < 1 || w < 1 || !L || !ab || !rgb) return IDC_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return IDC_ERR_CUDA;
+  return launch_lab2rgb(n, h, w, L, 0.0f, ab, rgb, (cudaStream_t)stream) == cudaSuccess ? IDC_OK : IDC_ERR_CUDA;
+}
+
+int idc_get_activation(idc_ctx* c, const char* name, float* out, size_t out_floats, int* ch, int* h, int* w) {
+  if (!c || !name) return IDC_ERR_ARG;
+  auto it = c->buf_index.find(name);
+  if (it == c->buf_index.end() || c->bufs[it->second].H == 0) return fail(c, IDC_ERR_KEY, "no activation '%s'", name);
+  const ActBuf& b = c->bufs[it->second];
+  if (ch) *ch = b.C;
+  if (h) *h = b.H;
+  if (w) *w = b.W;
+  if (!out) return IDC_OK;
+  const int n = c->last_n > 0 ? c->last_n : 1;
+  if (out_floats < (size_t)n * b.C * b.H * b.W) return fail(c, IDC_ERR_ARG, "output too small");
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  CUDA_TRY(c, launch_act_to_nchw(c, b, n, out, 0));
+  CUDA_TRY(c, cudaDeviceSynchronize());
+  return IDC_OK;
+}
+
+int idc_set_activation(idc_ctx* c, const char* name, int n, const float* in) {
+  if (!c || !name || !in || n < 1 || n > c->max_n) return IDC_ERR_ARG;
+  auto it = c->buf_index.find(name);
+  if (it == c->buf_index.end() || c->bufs[it->second].H == 0) return fail(c, IDC_ERR_KEY, "no activation '%s'", name);
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  CUDA_TRY(c, launch_nchw_to_act(c, c->bufs[it->second], n, in, 0));
+  CUDA_TRY(c, cudaDeviceSynchronize());
+  c->last_n = n;
+  return IDC_OK;
+}
+
+int idc_run_op(idc_ctx* c, const char* op_name, int n, void* stream) {
+  if (!c || !op_name || n < 1 || n > c->max_n) return IDC_ERR_ARG;
+  if (!c->weights_ready) return fail(c, IDC_ERR_STATE, "weights not finalized");
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  for (auto& op : c->ops)
+    if (op.name == op_name) {
+      if (op.fuse_out_head) return fail(c, IDC_ERR_ARG, "op %s has a fused head; use IDC_FLAG_KEEP_CONV10", op_name);
+      c->gadd_active = false;
+      if (c->simt) CUDA_TRY(c, simt_run_op(c, op, n, (cudaStream_t)stream));
+      else CUDA_TRY(c, umma_run_op(c, op, n, nullptr, 1.0f, (cudaStream_t)stream));
+      c->last_n = n;
+      return IDC_OK;
+    }
+  return fail(c, IDC_ERR_KEY, "no op '%s'", op_name);
+}
+
+int idc_num_ops(idc_ctx* c) { return c ? (int)c->ops.size() : 0; }
+const char* idc_op_name(idc_ctx* c, int i) {
+  return (c && i >= 0 && i < (int)c->ops.size()) ? c->ops[i].name.c_str() : nullptr;
+}
+int idc_last_launch_count(idc_ctx* c) { return c ? c->launch_count : 0; }
+
+double idc_flops_per_image(idc_ctx* c) {
+  if (!c) return 0;
+  double f = 2.0 * c->H * c->W * 64.0 * 36.0 + 2.0 * c->H * c->W * 2.0 * 128.0;  // model1.0 + model_out
+  for (auto& op : c->ops) f += op.flops_per_image;
+  return f;
+}
+
+const char* idc_last_error(idc_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
+
+int idc_destroy(idc_ctx* c) {
+  if (!c) return IDC_ERR_ARG;
+  cudaSetDevice(c->dev);
+  cudaDeviceSynchronize();
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  for (auto& op : c->ops) umma_free_op(op);
+  for (auto& b : c->bufs) { if (b.p0) cudaFree(b.p0); if (b.p1) cudaFree(b.p1); }
+  if (c->arena) cudaFree(c->arena);
+  if (c->logits) cudaFree(c->logits);
+  if (c->gvec) cudaFree(c->gvec);
+  if (c->gtmp) cudaFree(c->gtmp);
+  if (c->h_err) cudaFreeHost(c->h_err);
+  if (c->d_in) cudaFree(c->d_in);
+  if (c->d_out) cudaFree(c->d_out);
+  if (c->d_rgb) cudaFree(c->d_rgb);
+  if (c->h_in) cudaFreeHost(c->h_in);
+  if (c->h_out) cudaFreeHost(c->h_out);
+  if (c->h_rgb) cudaFreeHost(c->h_rgb);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return IDC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,371 @@
+// Bandwidth-bound kernels either side of the conv trunk:
+//   conv1_1_kernel    input pack (cat(L/100, ab/110, mask-maskcent), model.py:142-148) fused with
+//                     model1.0 (4->64 conv3x3 + ReLU, model.py:13-14)
+//   out_head_kernel   model_out 1x1 128->2 + tanh * 110 (model.py:108-109,175)  [unfused variant]
+//   softmax529_kernel softmax(0.2 * logits) over the 529 ab bins (model.py:131,160), NHWC->NCHW
+//   lab2rgb_kernel    lab2rgb_transpose (data/colorize_image.py:20-28): Lab -> sRGB uint8
+//   global_mlp_kernel global-hints branch (models/global_model/deploy_nodist.prototxt:38-172)
+//   act<->NCHW        test hooks
+#include "idc_internal.h"
+
+namespace idc {
+
+// ------------------------------------------------------------------------------------------
+// shared helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+// ------------------------------------------------------------------------------------------
+// conv1_1: one thread per pixel, 64 output channels in registers, weights broadcast from smem
+// ------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void __launch_bounds__(128) conv1_1_kernel(const float* __restrict__ L, const float* __restrict__ ab,
+                                                      const float* __restrict__ mask, float maskcent,
+                                                      const float* __restrict__ w, const float* __restrict__ b,
+                                                      int N, int H, int W, float* __restrict__ outf,
+                                                      __half* __restrict__ ohi, __half* __restrict__ olo) {
+  __shared__ __align__(16) float ws[36 * 64];
+  __shared__ float bs[64];
+  for (int i = threadIdx.x; i < 36 * 64; i += blockDim.x) ws[i] = w[i];
+  if (threadIdx.x < 64) bs[threadIdx.x] = b[threadIdx.x];
+  __syncthreads();
+  const size_t HW = (size_t)H * W;
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (size_t)N * HW) return;
+  const int n = (int)(pix / HW);
+  const int r = (int)(pix - (size_t)n * HW);
+  const int y = r / W, x = r - y * W;
+  float in[36];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int iy = y + ky - 1, ix = x + kx - 1;
+      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+      const size_t o = (size_t)iy * W + ix;
+      const int t = (ky * 3 + kx) * 4;
+      // zero padding applies to the concatenated, normalised input (model.py:148 then Conv2d pad)
+      in[t + 0] = ok ? __ldg(L + (size_t)n * HW + o) / 100.0f : 0.f;
+      in[t + 1] = ok ? __ldg(ab + (size_t)n * 2 * HW + o) / 110.0f : 0.f;
+      in[t + 2] = ok ? __ldg(ab + (size_t)n * 2 * HW + HW + o) / 110.0f : 0.f;
+      in[t + 3] = ok ? (__ldg(mask + (size_t)n * HW + o) - maskcent) : 0.f;
+    }
+  float acc[64];
+#pragma unroll
+  for (int c = 0; c < 64; ++c) acc[c] = bs[c];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) {
+    const float a = in[k];
+#pragma unroll
+    for (int c4 = 0; c4 < 16; ++c4) {
+      const float4 wv = *reinterpret_cast<const float4*>(&ws[k * 64 + c4 * 4]);
+      acc[c4 * 4 + 0] = fmaf(a, wv.x, acc[c4 * 4 + 0]);
+      acc[c4 * 4 + 1] = fmaf(a, wv.y, acc[c4 * 4 + 1]);
+      acc[c4 * 4 + 2] = fmaf(a, wv.z, acc[c4 * 4 + 2]);
+      acc[c4 * 4 + 3] = fmaf(a, wv.w, acc[c4 * 4 + 3]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 64; ++c) acc[c] = fmaxf(acc[c], 0.f);
+  if (!SPLIT) {
+    float4* op = reinterpret_cast<float4*>(outf + pix * 64);
+#pragma unroll
+    for (int c4 = 0; c4 < 16; ++c4) op[c4] = make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
+  } else {
+    uint4* oh = reinterpret_cast<uint4*>(ohi + pix * 64);
+    uint4* ol = reinterpret_cast<uint4*>(olo + pix * 64);
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+      __align__(16) __half h[8];
+      __align__(16) __half l[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_half(acc[c8 * 8 + j], h[j], l[j]);
+      oh[c8] = *reinterpret_cast<uint4*>(h);
+      if (olo) ol[c8] = *reinterpret_cast<uint4*>(l);   // olo == null in IDC_FLAG_FAST_FP16 mode
+    }
+  }
+}
+
+cudaError_t launch_conv1_1(Ctx* c, int n, const float* L, const float* ab, const float* mask, float maskcent,
+                           cudaStream_t st) {
+  const ActBuf& o = c->bufs[c->buf_index.at("a1_1")];
+  const size_t npix = (size_t)n * o.H * o.W;
+  const int grid = (int)((npix + 127) / 128);
+  if (c->simt)
+    conv1_1_kernel<false><<<grid, 128, 0, st>>>(L, ab, mask, maskcent, c->w11, c->b11, n, o.H, o.W,
+                                                static_cast<float*>(o.p0), nullptr, nullptr);
+  else
+    conv1_1_kernel<true><<<grid, 128, 0, st>>>(L, ab, mask, maskcent, c->w11, c->b11, n, o.H, o.W, nullptr,
+                                               static_cast<__half*>(o.p0), static_cast<__half*>(o.p1));
+  c->launch_count++;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// unfused regression head: 8 lanes per pixel, 16 channels each
+// ------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) out_head_kernel(const float* __restrict__ inf, const __half* __restrict__ ihi,
+                                                       const __half* __restrict__ ilo, const float* __restrict__ w,
+                                                       const float* __restrict__ b, int N, int H, int W,
+                                                       float* __restrict__ out) {
+  __shared__ float ws[256];
+  ws[threadIdx.x] = w[threadIdx.x];
+  __syncthreads();
+  const size_t HW = (size_t)H * W;
+  const size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int part = threadIdx.x & 7;
+  const bool valid = pix < (size_t)N * HW;
+  float s0 = 0.f, s1 = 0.f;
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int ch = part * 16 + j;
+      float v;
+      if (SPLIT) v = __half2float(ihi[pix * 128 + ch]) + (ilo ? __half2float(ilo[pix * 128 + ch]) : 0.f);
+      else v = inf[pix * 128 + ch];
+      s0 = fmaf(v, ws[ch], s0);
+      s1 = fmaf(v, ws[128 + ch], s1);
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if (valid && part == 0) {
+    const int n = (int)(pix / HW);
+    const size_t r = pix - (size_t)n * HW;
+    out[(size_t)n * 2 * HW + r] = tanhf(s0 + b[0]) * 110.0f;
+    out[(size_t)n * 2 * HW + HW + r] = tanhf(s1 + b[1]) * 110.0f;
+  }
+}
+
+cudaError_t launch_out_head(Ctx* c, int n, float* out_ab, cudaStream_t st) {
+  const ActBuf& in = c->bufs[c->buf_index.at("conv10_2")];
+  const size_t npix = (size_t)n * in.H * in.W;
+  const int grid = (int)((npix * 8 + 255) / 256);
+  if (c->simt)
+    out_head_kernel<false><<<grid, 256, 0, st>>>(static_cast<const float*>(in.p0), nullptr, nullptr, c->wout, c->bout,
+                                                 n, in.H, in.W, out_ab);
+  else
+    out_head_kernel<true><<<grid, 256, 0, st>>>(nullptr, static_cast<const __half*>(in.p0),
+                                                static_cast<const __half*>(in.p1), c->wout, c->bout, n, in.H, in.W,
+                                                out_ab);
+  c->launch_count++;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// softmax over 529 bins: block = 32 pixels; warp-reduce per pixel, transpose through smem so the
+// NCHW store is 128-byte coalesced.
+// ------------------------------------------------------------------------------------------
+constexpr int kBins = 529;
+__global__ void __launch_bounds__(256) softmax529_kernel(const float* __restrict__ logits, int ld, int M, int HW4,
+                                                         float* __restrict__ out) {
+  extern __shared__ float tile[];  // [529][33]
+  const int p0 = blockIdx.x * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int q = 0; q < 4; ++q) {
+    const int pl = warp * 4 + q;
+    const int p = p0 + pl;
+    if (p >= M) continue;
+    const float* row = logits + (size_t)p * ld;
+    float v[17];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 17; ++j) {
+      const int ch = lane + 32 * j;
+      v[j] = ch < kBins ? row[ch] * 0.2f : -INFINITY;   // model.py:160 "* .2"
+      mx = fmaxf(mx, v[j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 17; ++j) {
+      v[j] = (lane + 32 * j) < kBins ? expf(v[j] - mx) : 0.f;
+      sum += v[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int j = 0; j < 17; ++j) {
+      const int ch = lane + 32 * j;
+      if (ch < kBins) tile[ch * 33 + pl] = v[j] * inv;
+    }
+  }
+  __syncthreads();
+  // store: lanes run over the 32 pixels, warps over channels
+  const int p = p0 + lane;
+  if (p < M) {
+    const int n = p / HW4;
+    const int r = p - n * HW4;
+    float* ob = out + (size_t)n * kBins * HW4 + r;
+    for (int ch = warp; ch < kBins; ch += 8) ob[(size_t)ch * HW4] = tile[ch * 33 + lane];
+  }
+}
+
+cudaError_t launch_softmax529(Ctx* c, int n, float* out_dist, cudaStream_t st) {
+  const int HW4 = (c->H / 4) * (c->W / 4);
+  const int M = n * HW4;
+  int ld = 0;
+  for (auto& op : c->ops)
+    if (op.kind == OP_CLASS) ld = op.cout_pad;
+  const size_t smem = (size_t)kBins * 33 * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(softmax529_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  softmax529_kernel<<<ceil_div(M, 32), 256, smem, st>>>(c->logits, ld, M, HW4, out_dist);
+  c->launch_count++;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Lab -> sRGB uint8, float64 math like the reference's numpy/skimage path.
+// skimage 0.13 color.lab2rgb (lab2xyz + xyz2rgb), clip, *255, truncating cast
+// (data/colorize_image.py:27).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double lab_finv(double t) {
+  return t > 0.2068966 ? t * t * t : (t - 16.0 / 116.0) / 7.787;
+}
+__device__ __forceinline__ double srgb_gamma(double c) {
+  return c > 0.0031308 ? 1.055 * pow(c, 1.0 / 2.4) - 0.055 : 12.92 * c;
+}
+__global__ void lab2rgb_kernel(const float* __restrict__ L, float l_offset, const float* __restrict__ ab, int N,
+                               int HW, uint8_t* __restrict__ rgb) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * HW) return;
+  const int n = (int)(i / HW);
+  const size_t r = i - (size_t)n * HW;
+  const double l = (double)L[i] + (double)l_offset;
+  const double a = (double)ab[(size_t)n * 2 * HW + r];
+  const double b = (double)ab[(size_t)n * 2 * HW + HW + r];
+  const double fy = (l + 16.0) / 116.0;
+  const double fx = a / 500.0 + fy;
+  double fz = fy - b / 200.0;
+  if (fz < 0.0) fz = 0.0;
+  const double X = lab_finv(fx) * 0.95047, Y = lab_finv(fy) * 1.0, Z = lab_finv(fz) * 1.08883;
+  // inverse of the sRGB->XYZ matrix used by skimage (xyz_from_rgb), float64
+  const double m00 = 3.240481343200526, m01 = -1.5371515162713185, m02 = -0.4985363261688878;
+  const double m10 = -0.9692549499965682, m11 = 1.8759900014898907, m12 = 0.04155592655829284;
+  const double m20 = 0.05564663913517716, m21 = -0.20404133836651123, m22 = 1.0573110696453443;
+  double R = m00 * X + m01 * Y + m02 * Z;
+  double G = m10 * X + m11 * Y + m12 * Z;
+  double B = m20 * X + m21 * Y + m22 * Z;
+  R = srgb_gamma(R); G = srgb_gamma(G); B = srgb_gamma(B);
+  R = fmin(fmax(R, 0.0), 1.0) * 255.0;
+  G = fmin(fmax(G, 0.0), 1.0) * 255.0;
+  B = fmin(fmax(B, 0.0), 1.0) * 255.0;
+  rgb[i * 3 + 0] = (uint8_t)R;
+  rgb[i * 3 + 1] = (uint8_t)G;
+  rgb[i * 3 + 2] = (uint8_t)B;
+}
+
+cudaError_t launch_lab2rgb(int n, int h, int w, const float* L, float l_offset, const float* ab, uint8_t* rgb,
+                           cudaStream_t st) {
+  const size_t tot = (size_t)n * h * w;
+  lab2rgb_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(L, l_offset, ab, n, h * w, rgb);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// global-hints MLP: 4 x (1x1 conv = dense layer, ReLU, BN).  One warp per output neuron.
+// Layer 0 consumes [hist313, ind] (glob_conv1_1) and [s_avg, ind] (glob_s_conv1_1) summed.
+// ------------------------------------------------------------------------------------------
+__global__ void dense_relu_bn_kernel(const float* __restrict__ x, int xin, int xld, const float* __restrict__ w,
+                                     const float* __restrict__ b, const float* __restrict__ scale,
+                                     const float* __restrict__ shift, int cout, float* __restrict__ y, int yld) {
+  const int n = blockIdx.y;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= cout) return;
+  float s = 0.f;
+  for (int i = lane; i < xin; i += 32) s = fmaf(x[(size_t)n * xld + i], w[(size_t)o * xin + i], s);
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+  if (lane == 0) {
+    float v = fmaxf(s + b[o], 0.f);
+    y[(size_t)n * yld + o] = v * scale[o] + shift[o];
+  }
+}
+
+cudaError_t launch_global_mlp(Ctx* c, int n, const float* glob, cudaStream_t st) {
+  // layer 0: input 316 = [313 hist, 1 ind, 1 sat, 1 ind]; weight [512][316] (both branches concatenated)
+  const float* x = glob;
+  int xin = 316, xld = 316;
+  for (int l = 0; l < 4; ++l) {
+    float* y = (l == 3) ? c->gvec : c->gtmp + (size_t)(l & 1) * c->max_n * 512;
+    dim3 grid(512 / 8, n);
+    dense_relu_bn_kernel<<<grid, 256, 0, st>>>(x, xin, xld, c->gw[l], c->gb[l], c->gscale[l], c->gshift[l], 512, y,
+                                               512);
+    c->launch_count++;
+    x = y; xin = 512; xld = 512;
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// test hooks: activation <-> NCHW fp32
+// ------------------------------------------------------------------------------------------
+__global__ void act_to_nchw_kernel(const float* f, const __half* hi, const __half* lo, int N, int H, int W, int C,
+                                   float* out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t tot = (size_t)N * H * W * C;
+  if (i >= tot) return;
+  const int cch = (int)(i % C);
+  const size_t p = i / C;
+  const int x = (int)(p % W);
+  const int y = (int)((p / W) % H);
+  const int n = (int)(p / ((size_t)W * H));
+  const float v = f ? f[i] : (__half2float(hi[i]) + (lo ? __half2float(lo[i]) : 0.f));
+  out[(((size_t)n * C + cch) * H + y) * W + x] = v;
+}
+__global__ void nchw_to_act_kernel(const float* in, int N, int H, int W, int C, float* f, __half* hi, __half* lo) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t tot = (size_t)N * H * W * C;
+  if (i >= tot) return;
+  const int cch = (int)(i % C);
+  const size_t p = i / C;
+  const int x = (int)(p % W);
+  const int y = (int)((p / W) % H);
+  const int n = (int)(p / ((size_t)W * H));
+  const float v = in[(((size_t)n * C + cch) * H + y) * W + x];
+  if (f) f[i] = v;
+  else {
+    __half h, l;
+    split_half(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+cudaError_t launch_act_to_nchw(Ctx* c, const ActBuf& b, int n, float* out, cudaStream_t st) {
+  const size_t tot = (size_t)n * b.H * b.W * b.C;
+  if (c->simt)
+    act_to_nchw_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(static_cast<const float*>(b.p0), nullptr, nullptr, n,
+                                                               b.H, b.W, b.C, out);
+  else
+    act_to_nchw_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(nullptr, static_cast<const __half*>(b.p0),
+                                                               static_cast<const __half*>(b.p1), n, b.H, b.W, b.C, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_nchw_to_act(Ctx* c, const ActBuf& b, int n, const float* in, cudaStream_t st) {
+  const size_t tot = (size_t)n * b.H * b.W * b.C;
+  if (c->simt)
+    nchw_to_act_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(in, n, b.H, b.W, b.C, static_cast<float*>(b.p0),
+                                                               nullptr, nullptr);
+  else
+    nchw_to_act_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(in, n, b.H, b.W, b.C, nullptr,
+                                                               static_cast<__half*>(b.p0), static_cast<__half*>(b.p1));
+  return cudaGetLastError();
+}
+
+}  // namespace idc

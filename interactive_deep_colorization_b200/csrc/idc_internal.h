@@ -1,0 +1,162 @@
+// Internal declarations shared by the translation units of libidc_b200.so.
+// Layout vocabulary follows the reference network (model.py): blocks model1..model10,
+// activations conv1_2 ... conv10_2, hints, bins.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/idc_b200.h"
+
+namespace idc {
+
+constexpr int kMaxTaps = 13;  // fused up-layer: 4 deconv taps + 9 shortcut taps
+constexpr int kMaxCls = 4;    // output parity classes of a stride-2 transposed conv
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY02 = 2 };
+
+// One filter tap of a gather-GEMM convolution.  For logical output pixel (y, x) the tap reads
+// source pixel (y*s + ty, x*s + tx) of source `src`; out-of-range pixels read zero
+// (= the reference's zero padding).  (ky, kx) is the kernel index used for weight packing.
+struct Tap {
+  int src;  // 0 = main source, 1 = shortcut source
+  int ky, kx;
+  int ty, tx;
+};
+
+// Activation buffer.  SIMT engine: p0 = float [N,H,W,C].  tcgen05 engine: p0/p1 = __half
+// hi/lo planes, each [N,H,W,C]; value = hi + lo.
+struct ActBuf {
+  std::string name;
+  int H = 0, W = 0, C = 0;
+  void* p0 = nullptr;
+  void* p1 = nullptr;
+};
+
+// Per-output-channel epilogue vectors (device, fp32[cout_pad]).
+//   v = act(acc + bias) * scale + shift (+ gadd[n][c])
+// tcgen05 engine: weights are pre-scaled per output channel by a power of two 2^e (so the FP16 lo
+// term stays normal); bias is stored as bias*2^e and scale as scale*2^-e, which is exact and leaves
+// the formula unchanged because ReLU / LeakyReLU are positively homogeneous.
+struct Epilogue {
+  float* bias = nullptr;
+  float* scale = nullptr;  // BN gamma / sqrt(var + eps)   (1 when no BN)
+  float* shift = nullptr;  // BN beta - mean * scale        (0 when no BN)
+  int act = ACT_NONE;
+  bool has_bn = false;
+  bool gadd = false;  // add global-hints vector [N, cout] (row a15)
+};
+
+struct SrcDesc {
+  int buf = -1;  // index into Ctx::bufs
+  int s = 1;     // logical->source pixel stride (2 = read the ::2 decimation / the skip tensor)
+  int cin = 0;
+};
+
+enum OpKind { OP_CONV = 0, OP_UP = 1, OP_CLASS = 2 };
+
+struct ConvOp {
+  std::string name;
+  int kind = OP_CONV;
+  std::string wkey[2];  // state_dict keys: main conv / deconv, shortcut conv
+  std::string bnkey;
+  int nsrc = 1;
+  SrcDesc src[2];
+  int ncls = 1;
+  int ntaps = 0;                 // taps per class
+  Tap taps[kMaxCls][kMaxTaps];
+  int Hl = 0, Wl = 0;            // logical output grid (per class)
+  int out_buf = -1;
+  int os = 1;                    // output pixel = (y*os + cls/2, x*os + cls%2)
+  int cout = 0, cout_pad = 0;
+  int K = 0;                     // sum over taps of cin(src)
+  Epilogue epi;
+  bool fuse_out_head = false;    // tcgen05 engine: model_out (128->2, tanh*110) in the epilogue
+  bool out_f32 = false;          // store FP32 [M][cout_pad] instead of an activation (class logits)
+  // packed weights
+  float* w_simt = nullptr;       // [ncls][K][cout_pad] fp32
+  __half* w_hi = nullptr;        // [ncls*cout_pad][K] fp16 (x wscale)
+  __half* w_lo = nullptr;
+  // tcgen05 launch plan (filled by umma_plan_op)
+  int bn_tile = 0, hbox = 0, wbox = 0;
+  void* umma_plan = nullptr;
+  double flops_per_image = 0;
+};
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> dims;
+};
+
+struct Ctx {
+  int dev = 0;
+  int max_n = 0, H = 0, W = 0;
+  unsigned flags = 0;
+  bool simt = false, fast = false, dist = false, glob = false;
+  std::map<std::string, HostTensor> raw;
+  std::vector<ActBuf> bufs;
+  std::map<std::string, int> buf_index;
+  std::vector<ConvOp> ops;
+  // weight arena
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  bool weights_ready = false;
+  bool arena_laid_out = false;
+  // conv1_1 (4->64) + regression head + misc small weights (device fp32)
+  float* w11 = nullptr;   // [36][64]  k = tap*4 + cin
+  float* b11 = nullptr;   // [64]
+  float* wout = nullptr;  // [2][128]
+  float* bout = nullptr;  // [2]
+  // global hints MLP (device fp32)
+  float* gw[4] = {nullptr, nullptr, nullptr, nullptr};      // [cout][cin]
+  float* gb[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* gscale[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* gshift[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* gvec = nullptr;   // [max_n][512]
+  float* gtmp = nullptr;   // [2][max_n][512]
+  // workspace
+  float* logits = nullptr;     // [max_n*(H/4)*(W/4)][cout_pad(529)]
+  float* conv10_f32 = nullptr; // SIMT: conv10_2 is a normal buffer; unused otherwise
+  int* d_err = nullptr;        // watchdog flag (mapped pinned host memory: survives a device trap)
+  int* h_err = nullptr;
+  // staging for idc_forward_host
+  float* h_in = nullptr;  float* d_in = nullptr;   size_t in_floats = 0;
+  float* h_out = nullptr; float* d_out = nullptr;  size_t out_floats = 0;
+  uint8_t* h_rgb = nullptr; uint8_t* d_rgb = nullptr;
+  cudaStream_t own_stream = nullptr;
+  // CUDA graph cache for the batch-1 latency path
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_n = 0;
+  const void* graph_ptrs[8] = {nullptr};
+  float graph_maskcent = 0.f;
+  int launch_count = 0;
+  int graph_launches = 0;
+  bool gadd_active = false;     // a global-hints vector was supplied to this forward
+  int last_n = 0;
+  std::string err;
+};
+
+// ---- engine entry points (idc_simt.cu / idc_umma.cu / idc_heads.cu) ----
+cudaError_t simt_run_op(Ctx* c, ConvOp& op, int n, cudaStream_t st);
+int umma_plan_op(Ctx* c, ConvOp& op);              // builds tensor maps; returns IDC_* code
+void umma_free_op(ConvOp& op);
+cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float out_mult, cudaStream_t st);
+
+cudaError_t launch_conv1_1(Ctx* c, int n, const float* L, const float* ab, const float* mask,
+                           float maskcent, cudaStream_t st);
+cudaError_t launch_out_head(Ctx* c, int n, float* out_ab, cudaStream_t st);   // SIMT / KEEP_CONV10 path
+cudaError_t launch_softmax529(Ctx* c, int n, float* out_dist, cudaStream_t st);
+cudaError_t launch_lab2rgb(int n, int h, int w, const float* L, float l_offset, const float* ab,
+                           uint8_t* rgb, cudaStream_t st);
+cudaError_t launch_global_mlp(Ctx* c, int n, const float* glob, cudaStream_t st);
+cudaError_t launch_act_to_nchw(Ctx* c, const ActBuf& b, int n, float* out, cudaStream_t st);
+cudaError_t launch_nchw_to_act(Ctx* c, const ActBuf& b, int n, const float* in, cudaStream_t st);
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace idc

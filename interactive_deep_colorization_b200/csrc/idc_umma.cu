@@ -1,0 +1,599 @@
+// tcgen05 engine: implicit-GEMM convolution on the 5th-gen tensor cores (sm_100a).
+//
+//   D[128 pixels x BN couts] (FP32, TMEM) += A[128 x 64] (smem, K-major, SW128) * B[BN x 64]^T
+//
+// * A tiles are gathered by TMA straight from the NHWC activation planes: one 4-D box
+//   {64 ch, wbox, hbox, 1 image} per filter tap, shifted by the tap offset; out-of-bounds
+//   pixels are zero-filled by TMA (= the reference's zero padding), the `::2` decimation
+//   (model.py:149-151) and the output-parity views of the transposed convs are expressed as
+//   tensor-map strides, so no im2col / decimated copy ever exists in HBM.
+// * 1e-3 ab parity needs ~22 mantissa bits: activations and weights are stored as
+//   FP16 hi + lo planes and every product is issued as 3 MMAs (hi*hi + hi*lo + lo*hi) into the
+//   same FP32 TMEM accumulator.  IDC_FLAG_FAST_FP16 drops the lo planes (1 MMA).
+// * warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2-5 = epilogue
+//   (TMEM -> regs -> bias/act/BN/global-hints -> hi/lo split -> NHWC store, or the fused
+//   model_out head).  Two TMEM accumulators: epilogue(i) overlaps mainloop(i+1).  Persistent
+//   grid = min(tiles, #SM).
+#include <stdio.h>
+
+#include "idc_internal.h"
+
+namespace idc {
+
+constexpr int kBM = 128;      // pixels per tile (UMMA M)
+constexpr int kBK = 64;       // channels per k-block (128 bytes of FP16 = one SW128 row)
+constexpr int kThreads = 192;
+
+struct UmmaParams {
+  const CUtensorMap* amaps;  // device array, [view][hi, lo]
+  const int4* kblk;          // [ncls][nkb] : {map index (hi), c0, dy, dx}
+  int nkb, ncls;
+  int n_img, tiles_y, tiles_x, n_tiles_n, total_tiles;
+  int hbox, wbox, wshift;
+  int Hl, Wl, cout_pad;
+  const float* bias;   // bias / descale
+  const float* scale;  // bn_scale * descale
+  const float* shift;
+  const float* gadd;   // [n_img][gadd_ld] or null
+  int gadd_ld;
+  int act;
+  __half* out_hi;
+  __half* out_lo;
+  int Hout, Wout, Cout, os;
+  float* out_f32;      // logits [M][out_ld] or null
+  int out_ld;
+  const float* wout;   // fused head weights [2][128] or null
+  const float* bout;
+  float* out_ab;
+  float out_mult;
+  int* err;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug becomes an error code + trap instead of a hung GPU.
+__device__ __noinline__ void mbar_timeout(int* err, int code) {
+  if (err) {
+    atomicExch(err, code);
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 6000000000LL) mbar_timeout(err, code);
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 64 FP16 (128 B), 8-row swizzle atoms 1024 B
+// apart (SBO); LBO unused for a single K atom.  Bit layout = cute::UMMA::SmemDescriptor.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);  // start address
+  d |= (uint64_t)(1024u >> 4) << 32;            // stride byte offset
+  d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: A=B=F16, D=F32, both K-major, M=128, N=BN.
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+  return (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_h(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+template <int BN, bool SPLIT>
+struct SmemPlan {
+  static constexpr int kABytes = kBM * kBK * 2;                 // 16 KB
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kBBytes);
+  static constexpr int kTail = 3 * BN * 4 + 272 * 4 + kMaxCls * 80 * 16 + 256;  // epi vecs, head, kblk, barriers
+  static constexpr int kBudget = 232448 - 1024 - kTail;          // 227 KB opt-in limit minus alignment slack
+  static constexpr int kStages = kBudget / kStageBytes >= 4 ? 4 : kBudget / kStageBytes;
+  static constexpr int kTotal = kStages * kStageBytes + kTail + 1024;            // + alignment slack
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+};
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_constant__ CUtensorMap bmap_lo,
+                 const UmmaParams p) {
+  using SP = SmemPlan<BN, SPLIT>;
+  constexpr int STAGES = SP::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tail = smem + STAGES * SP::kStageBytes;
+  float* s_bias = reinterpret_cast<float*>(tail);
+  float* s_scale = s_bias + BN;
+  float* s_shift = s_scale + BN;
+  float* s_head = s_shift + BN;                                   // [2][128] + bias[2] (+pad)
+  int4* s_kblk = reinterpret_cast<int4*>(s_head + 272);           // [ncls][nkb] (<= 4*80)
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_kblk + kMaxCls * 80);
+  uint64_t* full_bar = s_bar;
+  uint64_t* empty_bar = s_bar + STAGES;
+  uint64_t* tfull_bar = s_bar + 2 * STAGES;
+  uint64_t* tempty_bar = s_bar + 2 * STAGES + 2;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- one-time setup ----
+  for (int i = threadIdx.x; i < p.ncls * p.nkb; i += kThreads) s_kblk[i] = p.kblk[i];
+  if (p.wout) {
+    for (int i = threadIdx.x; i < 256; i += kThreads) s_head[i] = p.wout[i];
+    if (threadIdx.x < 2) s_head[256 + threadIdx.x] = p.bout[threadIdx.x];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                 "r"((uint32_t)SP::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
+  const int tiles_per_cls = p.n_img * tiles_per_img * p.n_tiles_n;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int cls = tile / tiles_per_cls;
+        int r = tile - cls * tiles_per_cls;
+        const int nt = r % p.n_tiles_n;
+        r /= p.n_tiles_n;
+        const int img = r / tiles_per_img;
+        r -= img * tiles_per_img;
+        const int y0 = (r / p.tiles_x) * p.hbox, x0 = (r % p.tiles_x) * p.wbox;
+        const int brow = cls * p.cout_pad + nt * BN;
+        const int4* kb = s_kblk + cls * p.nkb;
+        for (int k = 0; k < p.nkb; ++k) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, SP::kStageBytes);
+          const int4 e = kb[k];
+          const uint32_t sa = smem_u32(smem + stage * SP::kStageBytes);
+          const CUtensorMap* am = p.amaps + e.x;
+          tma_load_4d(sa, am, fb, e.y, x0 + e.w, y0 + e.z, img);
+          if (SPLIT) tma_load_4d(sa + SP::kABytes, am + 1, fb, e.y, x0 + e.w, y0 + e.z, img);
+          const uint32_t sb = sa + (SPLIT ? 2 : 1) * SP::kABytes;
+          tma_load_2d(sb, &bmap_hi, fb, k * kBK, brow);
+          if (SPLIT) tma_load_2d(sb + SP::kBBytes, &bmap_lo, fb, k * kBK, brow);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int k = 0; k < p.nkb; ++k) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * SP::kStageBytes);
+          const uint32_t sb = sa + (SPLIT ? 2 : 1) * SP::kABytes;
+          const uint64_t a_hi = make_sw128_desc(sa);
+          const uint64_t b_hi = make_sw128_desc(sb);
+#pragma unroll
+          for (int kk = 0; kk < kBK / 16; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 2);  // 16 FP16 = 32 bytes = 2 descriptor units
+            if (SPLIT) {
+              const uint64_t a_lo = make_sw128_desc(sa + SP::kABytes);
+              const uint64_t b_lo = make_sw128_desc(sb + SP::kBBytes);
+              // small cross terms first, dominant term last
+              umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, (k | kk) ? 1u : 0u);
+              umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+            } else {
+              umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, (k | kk) ? 1u : 0u);
+            }
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&tfull_bar[acc]));      // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // =============================== epilogue (4 warps) ==========================
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;     // pixel row of the tile
+    const int et = threadIdx.x - 64;         // 0..127
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int cls = tile / tiles_per_cls;
+      int r = tile - cls * tiles_per_cls;
+      const int nt = r % p.n_tiles_n;
+      r /= p.n_tiles_n;
+      const int img = r / tiles_per_img;
+      r -= img * tiles_per_img;
+      const int y = (r / p.tiles_x) * p.hbox + (row >> p.wshift);
+      const int x = (r % p.tiles_x) * p.wbox + (row & (p.wbox - 1));
+      const bool valid = y < p.Hl && x < p.Wl;
+      const int n0 = nt * BN;
+      // stage this tile's per-channel epilogue vectors
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = et; i < BN; i += 128) {
+        s_bias[i] = p.bias[n0 + i];
+        s_scale[i] = p.scale[n0 + i];
+        s_shift[i] = p.shift[n0 + i] + (p.gadd ? p.gadd[(size_t)img * p.gadd_ld + n0 + i] : 0.f);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+
+      size_t opix = 0;
+      if (valid) {
+        if (p.out_f32) opix = ((size_t)(img * p.Hl + y) * p.Wl + x) * p.out_ld + n0;
+        else opix = ((size_t)(img * p.Hout + y * p.os + (cls >> 1)) * p.Wout + x * p.os + (cls & 1)) * p.Cout + n0;
+      }
+      float h0 = 0.f, h1 = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < BN; ch += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + ch, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = __uint_as_float(v[j]) + s_bias[ch + j];
+          if (p.act == ACT_RELU) t = fmaxf(t, 0.f);
+          else if (p.act == ACT_LEAKY02) t = t > 0.f ? t : 0.2f * t;
+          f[j] = fmaf(t, s_scale[ch + j], s_shift[ch + j]);
+        }
+        if (p.wout) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            h0 = fmaf(f[j], s_head[ch + j], h0);
+            h1 = fmaf(f[j], s_head[128 + ch + j], h1);
+          }
+        } else if (valid) {
+          if (p.out_f32) {
+            float4* o = reinterpret_cast<float4*>(p.out_f32 + opix + ch);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+          } else {
+            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + opix + ch);
+            uint4* ol = SPLIT ? reinterpret_cast<uint4*>(p.out_lo + opix + ch) : nullptr;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              __align__(16) __half hh[8];
+              __align__(16) __half ll[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (SPLIT) split_h(f[q * 8 + j], hh[j], ll[j]);
+                else hh[j] = __float2half_rn(f[q * 8 + j]);
+              }
+              oh[q] = *reinterpret_cast<uint4*>(hh);
+              if (SPLIT) ol[q] = *reinterpret_cast<uint4*>(ll);
+            }
+          }
+        }
+      }
+      // release the accumulator
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (p.wout && valid) {
+        // model_out: conv1x1(128->2) + tanh, x110 (model.py:108-109,175)
+        const size_t HW = (size_t)p.Hl * p.Wl;
+        const size_t o = (size_t)img * 2 * HW + (size_t)y * p.Wl + x;
+        p.out_ab[o] = tanhf(h0 + s_head[256]) * 110.0f * p.out_mult;
+        p.out_ab[o + HW] = tanhf(h1 + s_head[257]) * 110.0f * p.out_mult;
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)SP::kTmemCols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps + launch plan
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+struct UmmaPlan {
+  CUtensorMap* d_amaps = nullptr;
+  int4* d_kblk = nullptr;
+  CUtensorMap bmap_hi, bmap_lo;
+  UmmaParams prm{};
+  int num_sms = 148;
+};
+
+struct ViewKey {
+  int src, s, qy, qx;
+  bool operator==(const ViewKey& o) const { return src == o.src && s == o.s && qy == o.qy && qx == o.qx; }
+};
+
+static int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+
+template <int BN, bool SPLIT>
+static cudaError_t launch_inst(const UmmaPlan& pl, const UmmaParams& prm, cudaStream_t st) {
+  using SP = SmemPlan<BN, SPLIT>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SP::kTotal);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const int grid = prm.total_tiles < pl.num_sms ? prm.total_tiles : pl.num_sms;
+  umma_conv_kernel<BN, SPLIT><<<grid, kThreads, SP::kTotal, st>>>(pl.bmap_hi, pl.bmap_lo, prm);
+  return cudaGetLastError();
+}
+
+int umma_plan_op(Ctx* c, ConvOp& op) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { c->err = "cuTensorMapEncodeTiled entry point not available"; return IDC_ERR_CUDA; }
+  umma_free_op(op);
+  UmmaPlan* pl = new UmmaPlan();
+  op.umma_plan = pl;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, c->dev);
+  pl->num_sms = prop.multiProcessorCount;
+  // tile geometry
+  op.bn_tile = op.cout_pad == 64 ? 64 : op.cout_pad == 128 ? 128 : op.cout_pad == 576 ? 192 : 256;
+  if (op.cout_pad % op.bn_tile) { c->err = "cout not tileable: " + op.name; return IDC_ERR_ARG; }
+  int best = 1 << 30;
+  for (int wb = 128; wb >= 8; wb >>= 1) {
+    const int hb = kBM / wb;
+    const int t = ceil_div(op.Wl, wb) * ceil_div(op.Hl, hb);
+    if (t < best) { best = t; op.wbox = wb; op.hbox = hb; }
+  }
+  // views + k-block table
+  std::vector<ViewKey> views;
+  const int nkb = op.K / kBK;
+  std::vector<int4> kblk((size_t)op.ncls * nkb);
+  for (int cls = 0; cls < op.ncls; ++cls) {
+    int kb = 0;
+    for (int t = 0; t < op.ntaps; ++t) {
+      const Tap& tp = op.taps[cls][t];
+      const int s = op.src[tp.src].s;
+      ViewKey vk{tp.src, s, 0, 0};
+      int dy = tp.ty, dx = tp.tx;
+      if (s == 2) {
+        vk.qy = ((tp.ty % 2) + 2) % 2; vk.qx = ((tp.tx % 2) + 2) % 2;
+        dy = floordiv2(tp.ty); dx = floordiv2(tp.tx);
+      }
+      int vi = -1;
+      for (size_t i = 0; i < views.size(); ++i)
+        if (views[i] == vk) vi = (int)i;
+      if (vi < 0) { views.push_back(vk); vi = (int)views.size() - 1; }
+      const int cin = op.src[tp.src].cin;
+      if (cin % kBK) { c->err = "cin not a multiple of 64: " + op.name; return IDC_ERR_ARG; }
+      for (int c0 = 0; c0 < cin; c0 += kBK) kblk[(size_t)cls * nkb + kb++] = make_int4(vi * 2, c0, dy, dx);
+    }
+    if (kb != nkb) { c->err = "k-block count mismatch: " + op.name; return IDC_ERR_ARG; }
+  }
+  if (nkb > 80) { c->err = "too many k-blocks: " + op.name; return IDC_ERR_ARG; }
+  // A tensor maps
+  std::vector<CUtensorMap> amaps(views.size() * 2);
+  for (size_t i = 0; i < views.size(); ++i) {
+    const ViewKey& vk = views[i];
+    const ActBuf& b = c->bufs[op.src[vk.src].buf];
+    const int Hv = (b.H - vk.qy + vk.s - 1) / vk.s, Wv = (b.W - vk.qx + vk.s - 1) / vk.s;
+    for (int part = 0; part < 2; ++part) {
+      char* base = (char*)(part == 0 ? b.p0 : b.p1);
+      if (!base) { amaps[i * 2 + part] = amaps[i * 2]; continue; }  // fast mode: lo unused
+      base += ((size_t)vk.qy * b.W + vk.qx) * b.C * sizeof(__half);
+      cuuint64_t dims[4] = {(cuuint64_t)b.C, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)c->max_n};
+      cuuint64_t strides[3] = {(cuuint64_t)vk.s * b.C * 2, (cuuint64_t)vk.s * b.W * b.C * 2,
+                               (cuuint64_t)b.H * b.W * b.C * 2};
+      cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)op.wbox, (cuuint32_t)op.hbox, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = enc(&amaps[i * 2 + part], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        char msg[256];
+        snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled(A) failed (%d) for op %s view %zu", (int)r, op.name.c_str(), i);
+        c->err = msg;
+        return IDC_ERR_CUDA;
+      }
+    }
+  }
+  // B tensor maps: [ncls*cout_pad rows][K] FP16, K-major
+  for (int part = 0; part < 2; ++part) {
+    cuuint64_t dims[2] = {(cuuint64_t)op.K, (cuuint64_t)op.ncls * op.cout_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)op.K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)op.bn_tile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(part == 0 ? &pl->bmap_hi : &pl->bmap_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                     part == 0 ? (void*)op.w_hi : (void*)op.w_lo, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      char msg[256];
+      snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled(B) failed (%d) for op %s", (int)r, op.name.c_str());
+      c->err = msg;
+      return IDC_ERR_CUDA;
+    }
+  }
+  if (cudaMalloc(&pl->d_amaps, amaps.size() * sizeof(CUtensorMap)) != cudaSuccess ||
+      cudaMalloc(&pl->d_kblk, kblk.size() * sizeof(int4)) != cudaSuccess) {
+    c->err = "cudaMalloc failed in umma_plan_op";
+    return IDC_ERR_CUDA;
+  }
+  cudaMemcpy(pl->d_amaps, amaps.data(), amaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
+  cudaMemcpy(pl->d_kblk, kblk.data(), kblk.size() * sizeof(int4), cudaMemcpyHostToDevice);
+
+  UmmaParams& q = pl->prm;
+  q.amaps = pl->d_amaps; q.kblk = pl->d_kblk; q.nkb = nkb; q.ncls = op.ncls;
+  q.tiles_y = ceil_div(op.Hl, op.hbox); q.tiles_x = ceil_div(op.Wl, op.wbox);
+  q.n_tiles_n = op.cout_pad / op.bn_tile;
+  q.hbox = op.hbox; q.wbox = op.wbox;
+  q.wshift = 0;
+  while ((1 << q.wshift) < op.wbox) q.wshift++;
+  q.Hl = op.Hl; q.Wl = op.Wl; q.cout_pad = op.cout_pad;
+  q.bias = op.epi.bias; q.scale = op.epi.scale; q.shift = op.epi.shift;
+  q.gadd = nullptr; q.gadd_ld = 512;
+  q.act = op.epi.act;
+  if (op.out_f32) {
+    q.out_f32 = c->logits; q.out_ld = op.cout_pad;
+  } else if (op.out_buf >= 0) {
+    const ActBuf& ob = c->bufs[op.out_buf];
+    q.out_hi = (__half*)ob.p0; q.out_lo = (__half*)ob.p1;
+    q.Hout = ob.H; q.Wout = ob.W; q.Cout = ob.C; q.os = op.os;
+  }
+  if (op.fuse_out_head) { q.wout = c->wout; q.bout = c->bout; }
+  q.err = c->d_err;
+  return IDC_OK;
+}
+
+void umma_free_op(ConvOp& op) {
+  UmmaPlan* pl = static_cast<UmmaPlan*>(op.umma_plan);
+  if (!pl) return;
+  if (pl->d_amaps) cudaFree(pl->d_amaps);
+  if (pl->d_kblk) cudaFree(pl->d_kblk);
+  delete pl;
+  op.umma_plan = nullptr;
+}
+
+cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float out_mult, cudaStream_t st) {
+  UmmaPlan* pl = static_cast<UmmaPlan*>(op.umma_plan);
+  if (!pl) return cudaErrorInvalidValue;
+  UmmaParams prm = pl->prm;
+  prm.n_img = n;
+  prm.total_tiles = op.ncls * n * prm.tiles_y * prm.tiles_x * prm.n_tiles_n;
+  prm.gadd = (op.epi.gadd && c->gadd_active) ? c->gvec : nullptr;
+  prm.out_ab = out_ab_fused;
+  prm.out_mult = out_mult;
+  if (op.fuse_out_head && !out_ab_fused) return cudaErrorInvalidValue;
+  c->launch_count++;
+  const bool split = !c->fast;
+#define IDC_LAUNCH(BN_)                                                       \
+  return split ? launch_inst<BN_, true>(*pl, prm, st) : launch_inst<BN_, false>(*pl, prm, st)
+  switch (op.bn_tile) {
+    case 64: IDC_LAUNCH(64);
+    case 128: IDC_LAUNCH(128);
+    case 192: IDC_LAUNCH(192);
+    case 256: IDC_LAUNCH(256);
+    default: return cudaErrorInvalidValue;
+  }
+#undef IDC_LAUNCH
+}
+
+}  // namespace idc

@@ -1,0 +1,166 @@
+"""Thin Python handle on one `idc_ctx` (one device, one geometry).
+
+Host-side plumbing only: pointer marshalling, torch tensors as device memory, streams.
+All arithmetic of the forward happens in libidc_b200.so.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def _np_ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class LhnContext(object):
+    """Local Hints Network forward context (the B200 stand-in for
+    `SIGGRAPHGenerator(...).cuda().eval()`, /root/reference/data/colorize_image.py:221-232)."""
+
+    def __init__(self, device=0, max_n=1, H=256, W=256, dist=False, engine="tcgen05", fast_fp16=False,
+                 global_hints=False, use_graph=True, keep_conv10=False):
+        self.lib = _lib.load()
+        flags = 0
+        if dist:
+            flags |= _lib.FLAG_DIST
+        if engine == "simt":
+            flags |= _lib.FLAG_ENGINE_SIMT
+        elif engine != "tcgen05":
+            raise ValueError("engine must be 'tcgen05' or 'simt'")
+        if fast_fp16:
+            flags |= _lib.FLAG_FAST_FP16
+        if global_hints:
+            flags |= _lib.FLAG_GLOBAL_HINTS
+        if not use_graph:
+            flags |= _lib.FLAG_NO_GRAPH
+        if keep_conv10:
+            flags |= _lib.FLAG_KEEP_CONV10
+        self.device, self.max_n, self.H, self.W = int(device), int(max_n), int(H), int(W)
+        self.dist, self.global_hints, self.flags = bool(dist), bool(global_hints), flags
+        h = ctypes.c_void_p()
+        rc = self.lib.idc_create(self.device, self.max_n, self.H, self.W, flags, ctypes.byref(h))
+        if rc != _lib.IDC_OK:
+            raise _lib.IdcError(rc, "idc_create(device=%d, max_n=%d, %dx%d) failed -- a CUDA sm_100 device is "
+                                    "required; there is no CPU fallback" % (device, max_n, H, W))
+        self.h = h
+        self.ready = False
+
+    # ---- weights ---------------------------------------------------------------------------
+    def load_state_dict(self, sd):
+        """sd: {reference state_dict key: torch.Tensor | ndarray}.  Packs + uploads."""
+        for k, v in sd.items():
+            a = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+            if a.dtype == np.float32:
+                dt = _lib.F32
+            elif a.dtype == np.float64:
+                dt = _lib.F64
+            elif a.dtype == np.int64:
+                dt = _lib.I64
+            else:
+                a = a.astype(np.float32)
+                dt = _lib.F32
+            a = np.ascontiguousarray(a)
+            dims = (ctypes.c_int64 * max(a.ndim, 1))(*a.shape)
+            _lib.check(self.h, self.lib.idc_load_tensor(self.h, k.encode(), _np_ptr(a), dt, a.ndim, dims))
+        _lib.check(self.h, self.lib.idc_finalize_weights(self.h))
+        self.ready = True
+
+    def weights_arena(self):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _lib.check(self.h, self.lib.idc_weights_arena(self.h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def reserve_weights(self):
+        _lib.check(self.h, self.lib.idc_reserve_weights(self.h))
+
+    def adopt_weights(self):
+        _lib.check(self.h, self.lib.idc_adopt_weights(self.h))
+        self.ready = True
+
+    # ---- forward ---------------------------------------------------------------------------
+    def forward_device(self, L_mc, ab, mask, maskcent=0.0, glob=None, want_dist=False, want_rgb=False,
+                       out_ab=None, out_dist=None, out_rgb=None):
+        """torch CUDA float32 tensors [n,1,H,W], [n,2,H,W], [n,1,H,W] -> dict of torch tensors.
+        Asynchronous on torch's current stream."""
+        import torch
+        n = L_mc.shape[0]
+        for t in (L_mc, ab, mask):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        dev = L_mc.device
+        if out_ab is None:
+            out_ab = torch.empty((n, 2, self.H, self.W), dtype=torch.float32, device=dev)
+        if want_dist and out_dist is None:
+            out_dist = torch.empty((n, 529, self.H // 4, self.W // 4), dtype=torch.float32, device=dev)
+        if want_rgb and out_rgb is None:
+            out_rgb = torch.empty((n, self.H, self.W, 3), dtype=torch.uint8, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        rc = self.lib.idc_forward(self.h, n, self.H, self.W, L_mc.data_ptr(), ab.data_ptr(), mask.data_ptr(),
+                                  float(maskcent), glob.data_ptr() if glob is not None else None,
+                                  out_ab.data_ptr(), out_dist.data_ptr() if want_dist else None,
+                                  out_rgb.data_ptr() if want_rgb else None, st)
+        _lib.check(self.h, rc)
+        return {"ab": out_ab, "dist": out_dist if want_dist else None, "rgb": out_rgb if want_rgb else None}
+
+    def forward_host(self, L_mc, ab, mask, maskcent=0.0, glob=None, want_dist=False, want_rgb=False,
+                     out_ab=None, out_dist=None, out_rgb=None):
+        """numpy float32 C-contiguous host arrays (pinned or pageable) -> dict of numpy arrays.
+        Synchronous; includes H2D + D2H."""
+        n = L_mc.shape[0]
+        for a in (L_mc, ab, mask):
+            assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+        if out_ab is None:
+            out_ab = np.empty((n, 2, self.H, self.W), np.float32)
+        if want_dist and out_dist is None:
+            out_dist = np.empty((n, 529, self.H // 4, self.W // 4), np.float32)
+        if want_rgb and out_rgb is None:
+            out_rgb = np.empty((n, self.H, self.W, 3), np.uint8)
+        rc = self.lib.idc_forward_host(self.h, n, self.H, self.W, _np_ptr(L_mc), _np_ptr(ab), _np_ptr(mask),
+                                       float(maskcent), _np_ptr(glob) if glob is not None else None,
+                                       _np_ptr(out_ab), _np_ptr(out_dist) if want_dist else None,
+                                       _np_ptr(out_rgb) if want_rgb else None)
+        _lib.check(self.h, rc)
+        return {"ab": out_ab, "dist": out_dist if want_dist else None, "rgb": out_rgb if want_rgb else None}
+
+    # ---- introspection (tests) -------------------------------------------------------------
+    def op_names(self):
+        return [self.lib.idc_op_name(self.h, i).decode() for i in range(self.lib.idc_num_ops(self.h))]
+
+    def activation_shape(self, name):
+        c, h, w = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _lib.check(self.h, self.lib.idc_get_activation(self.h, name.encode(), None, 0, ctypes.byref(c),
+                                                       ctypes.byref(h), ctypes.byref(w)))
+        return c.value, h.value, w.value
+
+    def get_activation(self, name, n):
+        import torch
+        c, h, w = self.activation_shape(name)
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device="cuda:%d" % self.device)
+        _lib.check(self.h, self.lib.idc_get_activation(self.h, name.encode(), out.data_ptr(), out.numel(), None, None, None))
+        return out
+
+    def set_activation(self, name, t):
+        assert t.is_cuda and t.is_contiguous()
+        _lib.check(self.h, self.lib.idc_set_activation(self.h, name.encode(), t.shape[0], t.data_ptr()))
+
+    def run_op(self, op_name, n):
+        import torch
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.h, self.lib.idc_run_op(self.h, op_name.encode(), n, st))
+
+    def last_launch_count(self):
+        return self.lib.idc_last_launch_count(self.h)
+
+    def flops_per_image(self):
+        return self.lib.idc_flops_per_image(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.idc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

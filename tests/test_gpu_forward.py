@@ -1,0 +1,150 @@
+"""GPU: the tcgen05 engine end to end -- the parity tests proper.  Everything goes through
+the C ABI (engine.LhnContext -> libidc_b200.so)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import color_ref, synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+TOL_AB = 1e-3        # BASELINE.json north_star: ab within 1e-3 max-abs of the reference
+
+
+def _hints(case):
+    ab, m = np.zeros((2, 256, 256)), np.zeros((1, 256, 256))
+    if case == "kat":
+        synth.put_point(ab, m, [135, 160], 3, [23, -69])
+        synth.put_point(ab, m, [100, 160], 3, [0, 0])
+    elif case == "rand5":
+        ab, m = synth.synthetic_hints(256, 5, 0)
+    return ab, m
+
+
+@pytest.fixture(scope="module")
+def ctx256(synth_sd):
+    ctx = util.make_ctx(synth_sd, 256, 256, max_n=4, dist=True)
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("case,mc", [("zero", 0.0), ("rand5", 0.0), ("kat", 0.0), ("rand5", 0.5)])
+def test_golden_256(ctx256, case, mc):
+    """configs 1 and 2 of BASELINE.json: reference net output on mortar_pestle.jpg @256."""
+    g = util.golden("lhn_256.npz")
+    L = g["img_l_mc"].astype(np.float32)[None]
+    ab, m = _hints(case)
+    r = ctx256.forward_host(L, ab[None].astype(np.float32), m[None].astype(np.float32), mc, want_rgb=True)
+    ref = g["mc%d_%s_ab_raw" % (1 if mc else 0, case)]
+    err = util.maxabs(r["ab"][0], ref)
+    print("golden %s mc=%s max|dab| = %.3e" % (case, mc, err))
+    assert err <= TOL_AB, err
+    if not mc:
+        rgb_ref = g["mc0_%s_rgb" % case]
+        d = np.abs(r["rgb"][0].astype(int) - rgb_ref.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 2e-3, (d.max(), (d > 0).mean())
+
+
+def test_batch_64_oracle_and_layers(synth_sd):
+    L, ab, m = util.small_batch(3, 64, seed=300)
+    ctx = util.make_ctx(synth_sd, 64, 64, max_n=3, dist=True, keep_conv10=True)
+    r = ctx.forward_device(util.dev(L), util.dev(ab), util.dev(m), 0.5, want_dist=True)
+    torch.cuda.synchronize()
+    (reg, dist), inter = util.oracle_forward(synth_sd, L, ab, m, 0.5, dist=True, intermediates=True)
+    for name in ["a1_1", "conv1_2", "conv2_2", "conv3_3", "conv4_3", "conv5_3", "conv6_3", "conv7_3", "conv8_3",
+                 "conv9_3", "a10_1", "conv10_2"]:
+        err = util.maxabs(ctx.get_activation(name, 3), inter[name])
+        assert err < 2e-4, (name, err)
+    assert util.maxabs(r["ab"], reg) <= TOL_AB
+    assert util.maxabs(r["dist"], dist) < 1e-5
+    assert abs(float(r["dist"].sum(1).mean()) - 1.0) < 1e-5
+    ctx.close()
+    # fused-head variant (default) must agree with the unfused one
+    ctx2 = util.make_ctx(synth_sd, 64, 64, max_n=3)
+    r2 = ctx2.forward_device(util.dev(L), util.dev(ab), util.dev(m), 0.5)
+    torch.cuda.synchronize()
+    assert util.maxabs(r2["ab"], r["ab"]) < 1e-4
+    ctx2.close()
+
+
+def test_dist_golden(ctx256):
+    g = util.golden("lhn_256.npz")
+    gd = util.golden("lhn_dist_256.npz")
+    L = g["img_l_mc"].astype(np.float32)[None]
+    ab, m = _hints("rand5")
+    r = ctx256.forward_host(L, ab[None].astype(np.float32), m[None].astype(np.float32), 0.5, want_dist=True)
+    d = r["dist"][0]
+    assert util.maxabs(d[:, ::8, ::8], gd["dist_rows"]) < 1e-5
+    assert util.maxabs(d.sum(0), gd["dist_sum64"]) < 1e-5
+    assert util.maxabs(d.max(0), gd["dist_max64"]) < 1e-5
+    assert (d.argmax(0) == gd["dist_argmax64"]).mean() > 0.999
+    assert util.maxabs(r["ab"][0] * 110.0, gd["ret_quirk"]) < 0.15      # quirk q1: tanh*110*110
+
+
+def test_lab2rgb_kernel_bit_exact():
+    from interactive_deep_colorization_b200 import _lib
+    lib = _lib.load()
+    rs = np.random.RandomState(3)
+    L = rs.uniform(0, 100, (2, 1, 64, 96)).astype(np.float32)
+    ab = rs.uniform(-110, 110, (2, 2, 64, 96)).astype(np.float32)
+    dL, dab = util.dev(L), util.dev(ab)
+    out = torch.empty((2, 64, 96, 3), dtype=torch.uint8, device="cuda")
+    rc = lib.idc_lab2rgb_u8(0, 2, 64, 96, dL.data_ptr(), dab.data_ptr(), out.data_ptr(), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    for i in range(2):
+        ref = color_ref.lab2rgb_transpose(L[i].astype(np.float64), ab[i].astype(np.float64))
+        assert np.array_equal(out[i].cpu().numpy(), ref)
+
+
+def test_wrapper_api_end_to_end(synth_sd):
+    """ColorizeImageB200 / ...Dist used exactly like the reference notebook uses ColorizeImageTorch."""
+    from interactive_deep_colorization_b200 import colorize_image as CI
+    g = util.golden("lhn_256.npz")
+    cm = CI.ColorizeImageB200(Xd=256)
+    cm.prep_net(state_dict=synth_sd)
+    cm.set_image(g["img_rgb"])
+    ab, m = np.zeros((2, 256, 256)), np.zeros((1, 256, 256))
+    CI.put_point(ab, m, [135, 160], 3, [23, -69])
+    CI.put_point(ab, m, [100, 160], 3, [0, 0])
+    rgb = cm.net_forward(ab, m)
+    assert rgb.shape == (256, 256, 3) and rgb.dtype == np.uint8
+    assert util.maxabs(cm.output_ab_raw, g["mc0_kat_ab_raw"]) <= TOL_AB
+    d = np.abs(rgb.astype(int) - g["mc0_kat_rgb"].astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 2e-3
+    assert np.max(np.abs(cm.output_ab - g["mc0_kat_output_ab"])) < 1.5     # 1 uint8 step in ab units
+    assert cm.get_img_fullres().shape == (256, 256, 3)
+    cd = CI.ColorizeImageB200Dist(Xd=256, maskcent=True)
+    cd.prep_net(state_dict=synth_sd)
+    cd.set_image(g["img_rgb"])
+    a5, m5 = synth.synthetic_hints(256, 5, 0)
+    ret = cd.net_forward(a5, m5)
+    gd = util.golden("lhn_dist_256.npz")
+    assert util.maxabs(ret, gd["ret_quirk"]) < 0.15
+    np.random.seed(0)
+    reccs = cd.get_ab_reccs(128, 128, K=9, N=25000)
+    assert reccs.shape == (9, 2) and np.all(np.abs(reccs) <= 110)
+
+
+def test_full_size_batch_properties(synth_sd):
+    """BASELINE config 3 size (64 x 256^2): size-independent properties instead of an oracle run:
+    (1) every image of the batch equals the same image run alone (no cross-image leakage),
+    (2) batch permutation equivariance, (3) outputs bounded by tanh*110."""
+    N = 64
+    L, ab, m = synth.synthetic_batch(N, 256, seed=0, max_hints=10)
+    ctx = util.make_ctx(synth_sd, 256, 256, max_n=N)
+    dL, dab, dm = util.dev(L), util.dev(ab), util.dev(m)
+    out = ctx.forward_device(dL, dab, dm, 0.5)["ab"].clone()
+    perm = torch.randperm(N, generator=torch.Generator().manual_seed(0)).cuda()
+    out_p = ctx.forward_device(dL[perm].contiguous(), dab[perm].contiguous(), dm[perm].contiguous(), 0.5)["ab"]
+    torch.cuda.synchronize()
+    assert torch.equal(out_p, out[perm])
+    assert float(out.abs().max()) <= 110.0
+    for i in (0, 17, 63):
+        single = ctx.forward_device(dL[i:i + 1].contiguous(), dab[i:i + 1].contiguous(), dm[i:i + 1].contiguous(), 0.5)["ab"]
+        torch.cuda.synchronize()
+        assert torch.equal(single[0], out[i])
+    # spot parity against the oracle on two images of the batch
+    ref = util.oracle_forward(synth_sd, L[[5, 40]], ab[[5, 40]], m[[5, 40]], 0.5)
+    assert util.maxabs(out[[5, 40]], ref) <= TOL_AB
+    ctx.close()

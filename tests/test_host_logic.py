@@ -1,0 +1,73 @@
+"""CPU: host-side mirror of the reference wrapper (no GPU work)."""
+import numpy as np
+
+from interactive_deep_colorization_b200 import colorize_image as CI
+from interactive_deep_colorization_b200.model import SIGGRAPHGeneratorB200
+from oracle import color_ref, synth
+from tests import util
+
+
+def test_preconditions_return_minus_one(capsys):
+    cm = CI.ColorizeImageB200(Xd=64)
+    ab, m = np.zeros((2, 64, 64)), np.zeros((1, 64, 64))
+    assert cm.net_forward(ab, m) == -1                  # reference :85-87
+    assert "image" in capsys.readouterr().out
+    cm.set_image(np.zeros((64, 64, 3), np.uint8))
+    assert cm.net_forward(ab, m) == -1                  # reference :88-90
+    assert "net" in capsys.readouterr().out
+
+
+def test_image_prep_matches_reference_golden():
+    g = util.golden("lhn_256.npz")
+    cm = CI.ColorizeImageB200(Xd=256)
+    cm.set_image(g["img_rgb"])
+    assert np.max(np.abs(cm.img_l_mc - g["img_l_mc"])) < 1e-9
+    assert cm.img_l.shape == (1, 256, 256) and cm.img_ab.shape == (2, 256, 256)
+    assert cm.get_img_gray().shape == (256, 256, 3)
+    # quantised output_ab path (reference :196-198)
+    cm.output_rgb = g["mc0_kat_rgb"]
+    cm._set_out_ab_()
+    assert np.max(np.abs(cm.output_ab - g["mc0_kat_output_ab"])) < 1e-4
+    # full-res rendering: img_rgb_fullres == img_rgb here, so zoom factor is 1
+    assert np.array_equal(cm.get_img_fullres(), color_ref.lab2rgb_transpose(cm.img_l, cm.output_ab))
+
+
+def test_put_point_and_hint_normalisation():
+    ab, m = np.zeros((2, 256, 256)), np.zeros((1, 256, 256))
+    CI.put_point(ab, m, [135, 160], 3, [23, -69])
+    assert m.sum() == 49 and ab[0, 135, 160] == 23 and ab[1, 132, 163] == -69 and ab[0, 131, 160] == 0
+    cm = CI.ColorizeImageB200(Xd=256, maskcent=True)
+    assert cm.mask_cent == .5 and cm.mask_mult == 1. and cm.l_mean == 50.
+    cm.img_l_set = cm.net_set = True
+    assert CI.ColorizeImageBase.net_forward(cm, ab, m) == 0
+    assert np.array_equal(cm.input_ab_mc, ab) and np.array_equal(cm.input_mask_mult, m)
+
+
+def test_state_dict_keys_match_synthetic_reference_keys():
+    sd = synth.synthetic_state_dict()
+    net = SIGGRAPHGeneratorB200(dist=True)
+    own = net.state_dict()
+    assert set(own.keys()) == set(sd.keys())
+    for k, v in sd.items():
+        assert tuple(own[k].shape) == tuple(v.shape), k
+
+
+def test_lazy_upsampled_dist():
+    d64 = np.random.RandomState(0).rand(529, 4, 4).astype(np.float32)
+    lazy = CI._LazyUpsampledDist(d64)
+    full = np.repeat(np.repeat(d64, 4, 1), 4, 2)
+    assert lazy.shape == (529, 16, 16)
+    assert np.array_equal(lazy[:, 7, 9], full[:, 7, 9])
+    assert np.array_equal(np.asarray(lazy), full)
+
+
+def test_reccs_are_sorted_by_mass():
+    cd = CI.ColorizeImageB200Dist(Xd=16)
+    pmf = np.zeros(529, np.float32)
+    pmf[[10, 300, 500]] = [0.6, 0.3, 0.1]
+    cd.dist_ab = CI._LazyUpsampledDist(np.tile(pmf[:, None, None], (1, 4, 4)))
+    cd.dist_ab_set = True
+    np.random.seed(0)
+    centers, conf = cd.get_ab_reccs(5, 5, K=3, N=5000, return_conf=True)
+    assert np.allclose(centers[0], cd.pts_in_hull[10]) and np.allclose(centers[2], cd.pts_in_hull[500])
+    assert conf[0] > conf[1] > conf[2] and abs(conf.sum() - 1) < 1e-9
