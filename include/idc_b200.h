@@ -125,6 +125,15 @@ int idc_set_activation(idc_ctx* ctx, const char* name, int n, const float* in_nc
 int idc_run_op(idc_ctx* ctx, const char* op_name, int n, void* stream);
 int idc_num_ops(idc_ctx* ctx);
 const char* idc_op_name(idc_ctx* ctx, int i);
+/* Per-op device timing (CUDA events on the forward's stream, recorded between the op launches).
+ * idc_set_profiling(ctx, 1) starts accumulating over subsequent forwards; idc_get_profile
+ * synchronises, writes the MEAN milliseconds per forward of slot i into ms[i] (slot 0 = fused
+ * pack+conv1_1, slots 1..num_ops = the ops in idc_op_name order, last slot = heads/post) and resets.
+ * Returns the number of slots (num_ops + 2) or <0. */
+int idc_set_profiling(idc_ctx* ctx, int enable);
+int idc_get_profile(idc_ctx* ctx, float* ms, int max_slots);
+/* FLOPs (2*MACs) of op i for ONE image (0 for out-of-range i) */
+double idc_op_flops(idc_ctx* ctx, int i);
 /* kernels launched by the last forward (gpu_launches in bench.py) */
 int idc_last_launch_count(idc_ctx* ctx);
 /* FLOPs (2*MACs, conv+deconv) of one image at the ctx geometry; includes model_class iff DIST */

@@ -39,6 +39,9 @@ SYMBOLS = [
     ("idc_run_op", _c.c_int, [_P, _c.c_char_p, _c.c_int, _P]),
     ("idc_num_ops", _c.c_int, [_P]),
     ("idc_op_name", _c.c_char_p, [_P, _c.c_int]),
+    ("idc_set_profiling", _c.c_int, [_P, _c.c_int]),
+    ("idc_get_profile", _c.c_int, [_P, _c.POINTER(_c.c_float), _c.c_int]),
+    ("idc_op_flops", _c.c_double, [_P, _c.c_int]),
     ("idc_last_launch_count", _c.c_int, [_P]),
     ("idc_flops_per_image", _c.c_double, [_P]),
     ("idc_last_error", _c.c_char_p, [_P]),

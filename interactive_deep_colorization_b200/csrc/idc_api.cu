@@ -351,8 +351,11 @@ int pack_weights(Ctx* c, char* host) {
           e = std::max(-24, std::min(24, e));
         }
         const float sc = ldexpf(1.f, e);
-        bias[co] *= sc;                 // exact (power of two)
-        scale[co] *= ldexpf(1.f, -e);
+        // acc = sum (a * 2^S)(w * 2^e); stored output = v * 2^Sout  (all exact powers of two)
+        const int sout = (op.out_f32 || op.fuse_out_head) ? 0 : kActScaleLog2;
+        bias[co] = ldexpf(bias[co], e + kActScaleLog2);
+        scale[co] = ldexpf(scale[co], -(e + kActScaleLog2) + sout);
+        shift[co] = ldexpf(shift[co], sout);
         for (int cls = 0; cls < op.ncls; ++cls) {
           int k0 = 0;
           for (int t = 0; t < op.ntaps; ++t) {
@@ -423,14 +426,27 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
                 float* out_ab, float* out_dist, uint8_t* out_rgb, cudaStream_t st) {
   c->launch_count = 0;
   c->gadd_active = false;
+  std::vector<cudaEvent_t>* ev = nullptr;
+  auto mark = [&]() {
+    if (!ev) return;
+    cudaEvent_t e;
+    if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev->push_back(e);
+  };
+  if (c->profiling) { c->prof_runs.emplace_back(); ev = &c->prof_runs.back(); }
+  mark();
   if (glob && c->glob) {
     CUDA_TRY(c, launch_global_mlp(c, n, glob, st));
     c->gadd_active = true;
   }
   CUDA_TRY(c, launch_conv1_1(c, n, L, ab, mask, maskcent, st));
+  mark();
   for (auto& op : c->ops) {
     if (c->simt) CUDA_TRY(c, simt_run_op(c, op, n, st));
     else CUDA_TRY(c, umma_run_op(c, op, n, op.fuse_out_head ? out_ab : nullptr, 1.0f, st));
+    mark();
   }
   const bool fused = !c->simt && !(c->flags & IDC_FLAG_KEEP_CONV10);
   if (!fused) CUDA_TRY(c, launch_out_head(c, n, out_ab, st));
@@ -439,6 +455,7 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
     CUDA_TRY(c, launch_lab2rgb(n, c->H, c->W, L, 50.0f, out_ab, out_rgb, st));
     c->launch_count++;
   }
+  mark();
   c->last_n = n;
   return IDC_OK;
 }
@@ -609,8 +626,11 @@ int idc_forward_host(idc_ctx* c, int n, int h, int w, const float* L, const floa
       if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
       cudaGraph_t g = nullptr;
       CUDA_TRY(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const bool prof = c->profiling;
+      c->profiling = false;            // event timing is meaningless inside a capture
       rc = run_forward(c, n, dL, dab, dmask, maskcent, want_glob ? dglob : nullptr, dout, want_dist ? ddist : nullptr,
                        want_rgb ? c->d_rgb : nullptr, st);
+      c->profiling = prof;
       cudaError_t ce = cudaStreamEndCapture(st, &g);
       if (rc != IDC_OK) { if (g) cudaGraphDestroy(g); return rc; }
       CUDA_TRY(c, ce);
@@ -693,6 +713,40 @@ int idc_run_op(idc_ctx* c, const char* op_name, int n, void* stream) {
   return fail(c, IDC_ERR_KEY, "no op '%s'", op_name);
 }
 
+int idc_set_profiling(idc_ctx* c, int enable) {
+  if (!c) return IDC_ERR_ARG;
+  c->profiling = enable != 0;
+  return IDC_OK;
+}
+
+int idc_get_profile(idc_ctx* c, float* ms, int max_slots) {
+  if (!c || !ms) return IDC_ERR_ARG;
+  const int slots = (int)c->ops.size() + 2;
+  if (max_slots < slots) return fail(c, IDC_ERR_ARG, "need %d slots", slots);
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  CUDA_TRY(c, cudaDeviceSynchronize());
+  for (int i = 0; i < slots; ++i) ms[i] = 0.f;
+  int runs = 0;
+  for (auto& ev : c->prof_runs) {
+    if ((int)ev.size() == slots + 1) {
+      for (int i = 0; i < slots; ++i) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+        ms[i] += t;
+      }
+      runs++;
+    }
+    for (cudaEvent_t e : ev) c->prof_pool.push_back(e);
+  }
+  c->prof_runs.clear();
+  if (runs) for (int i = 0; i < slots; ++i) ms[i] /= runs;
+  return slots;
+}
+
+double idc_op_flops(idc_ctx* c, int i) {
+  return (c && i >= 0 && i < (int)c->ops.size()) ? c->ops[i].flops_per_image : 0.0;
+}
+
 int idc_num_ops(idc_ctx* c) { return c ? (int)c->ops.size() : 0; }
 const char* idc_op_name(idc_ctx* c, int i) {
   return (c && i >= 0 && i < (int)c->ops.size()) ? c->ops[i].name.c_str() : nullptr;
@@ -714,6 +768,8 @@ int idc_destroy(idc_ctx* c) {
   cudaDeviceSynchronize();
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   for (auto& op : c->ops) umma_free_op(op);
+  for (auto& ev : c->prof_runs) for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   for (auto& b : c->bufs) { if (b.p0) cudaFree(b.p0); if (b.p1) cudaFree(b.p1); }
   if (c->arena) cudaFree(c->arena);
   if (c->logits) cudaFree(c->logits);

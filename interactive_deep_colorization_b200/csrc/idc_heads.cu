@@ -14,6 +14,7 @@ namespace idc {
 // shared helpers
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
+  v = fminf(fmaxf(v, -65504.f), 65504.f);
   hi = __float2half_rn(v);
   lo = __float2half_rn(v - __half2float(hi));
 }
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(128) conv1_1_kernel(const float* __restrict__ 
       __align__(16) __half h[8];
       __align__(16) __half l[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) split_half(acc[c8 * 8 + j], h[j], l[j]);
+      for (int j = 0; j < 8; ++j) split_half(acc[c8 * 8 + j] * kActScale, h[j], l[j]);
       oh[c8] = *reinterpret_cast<uint4*>(h);
       if (olo) ol[c8] = *reinterpret_cast<uint4*>(l);   // olo == null in IDC_FLAG_FAST_FP16 mode
     }
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) out_head_kernel(const float* __restrict__
     for (int j = 0; j < 16; ++j) {
       const int ch = part * 16 + j;
       float v;
-      if (SPLIT) v = __half2float(ihi[pix * 128 + ch]) + (ilo ? __half2float(ilo[pix * 128 + ch]) : 0.f);
+      if (SPLIT) v = (__half2float(ihi[pix * 128 + ch]) + (ilo ? __half2float(ilo[pix * 128 + ch]) : 0.f)) * kActInvScale;
       else v = inf[pix * 128 + ch];
       s0 = fmaf(v, ws[ch], s0);
       s1 = fmaf(v, ws[128 + ch], s1);
@@ -324,7 +325,7 @@ __global__ void act_to_nchw_kernel(const float* f, const __half* hi, const __hal
   const int x = (int)(p % W);
   const int y = (int)((p / W) % H);
   const int n = (int)(p / ((size_t)W * H));
-  const float v = f ? f[i] : (__half2float(hi[i]) + (lo ? __half2float(lo[i]) : 0.f));
+  const float v = f ? f[i] : (__half2float(hi[i]) + (lo ? __half2float(lo[i]) : 0.f)) * kActInvScale;
   out[(((size_t)n * C + cch) * H + y) * W + x] = v;
 }
 __global__ void nchw_to_act_kernel(const float* in, int N, int H, int W, int C, float* f, __half* hi, __half* lo) {
@@ -340,7 +341,7 @@ __global__ void nchw_to_act_kernel(const float* in, int N, int H, int W, int C, 
   if (f) f[i] = v;
   else {
     __half h, l;
-    split_half(v, h, l);
+    split_half(v * kActScale, h, l);
     hi[i] = h;
     if (lo) lo[i] = l;
   }

@@ -20,6 +20,14 @@ constexpr int kMaxCls = 4;    // output parity classes of a stride-2 transposed 
 
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY02 = 2 };
 
+// tcgen05 engine: activations are stored as FP16 hi/lo planes of (value * 2^kActScaleLog2).
+// Measured on B200 (round 1): the tensor core treats FP16 *subnormal* operands as zero, so an
+// unscaled lo plane loses the low half of every activation below 0.125 (ab error 1.2e-2 instead
+// of 1e-4).  Scaling by 64 keeps lo normal down to |a| = 0.002; FP16 range then covers |a| < 1023.
+constexpr int kActScaleLog2 = 6;
+constexpr float kActScale = 64.0f;
+constexpr float kActInvScale = 1.0f / 64.0f;
+
 // One filter tap of a gather-GEMM convolution.  For logical output pixel (y, x) the tap reads
 // source pixel (y*s + ty, x*s + tx) of source `src`; out-of-range pixels read zero
 // (= the reference's zero padding).  (ky, kx) is the kernel index used for weight packing.
@@ -138,6 +146,10 @@ struct Ctx {
   int graph_launches = 0;
   bool gadd_active = false;     // a global-hints vector was supplied to this forward
   int last_n = 0;
+  // per-op profiling
+  bool profiling = false;
+  std::vector<std::vector<cudaEvent_t>> prof_runs;   // one event list per profiled forward
+  std::vector<cudaEvent_t> prof_pool;
   std::string err;
 };
 

@@ -36,6 +36,7 @@ struct UmmaParams {
   const float* shift;
   const float* gadd;   // [n_img][gadd_ld] or null
   int gadd_ld;
+  float gadd_mult;     // output activation scale (2^kActScaleLog2) applied to the global-hints vector
   int act;
   __half* out_hi;
   __half* out_lo;
@@ -148,6 +149,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 }
 
 __device__ __forceinline__ void split_h(float v, __half& hi, __half& lo) {
+  v = fminf(fmaxf(v, -65504.f), 65504.f);
   hi = __float2half_rn(v);
   lo = __float2half_rn(v - __half2float(hi));
 }
@@ -314,7 +316,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       for (int i = et; i < BN; i += 128) {
         s_bias[i] = p.bias[n0 + i];
         s_scale[i] = p.scale[n0 + i];
-        s_shift[i] = p.shift[n0 + i] + (p.gadd ? p.gadd[(size_t)img * p.gadd_ld + n0 + i] : 0.f);
+        s_shift[i] = p.shift[n0 + i] + (p.gadd ? p.gadd[(size_t)img * p.gadd_ld + n0 + i] * p.gadd_mult : 0.f);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
 
@@ -549,7 +551,7 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   while ((1 << q.wshift) < op.wbox) q.wshift++;
   q.Hl = op.Hl; q.Wl = op.Wl; q.cout_pad = op.cout_pad;
   q.bias = op.epi.bias; q.scale = op.epi.scale; q.shift = op.epi.shift;
-  q.gadd = nullptr; q.gadd_ld = 512;
+  q.gadd = nullptr; q.gadd_ld = 512; q.gadd_mult = kActScale;
   q.act = op.epi.act;
   if (op.out_f32) {
     q.out_f32 = c->logits; q.out_ld = op.cout_pad;

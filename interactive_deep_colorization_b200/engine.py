@@ -148,6 +148,19 @@ class LhnContext(object):
         st = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.h, self.lib.idc_run_op(self.h, op_name.encode(), n, st))
 
+    def set_profiling(self, on):
+        _lib.check(self.h, self.lib.idc_set_profiling(self.h, 1 if on else 0))
+
+    def get_profile(self):
+        """-> list of (slot name, mean ms per forward, FLOPs per image) since profiling was enabled."""
+        names = ["pack+conv1_1"] + self.op_names() + ["heads+post"]
+        buf = (ctypes.c_float * len(names))()
+        rc = self.lib.idc_get_profile(self.h, buf, len(names))
+        if rc < 0:
+            _lib.check(self.h, rc)
+        flops = [2.0 * self.H * self.W * 64 * 36] + [self.lib.idc_op_flops(self.h, i) for i in range(len(names) - 2)] + [0.0]
+        return [(names[i], float(buf[i]), flops[i]) for i in range(len(names))]
+
     def last_launch_count(self):
         return self.lib.idc_last_launch_count(self.h)
 
