@@ -182,19 +182,21 @@ def run_ours(args):
     value = world * N / (ms_step * 1e-3)
 
     # ---- end to end through the host-pointer C-ABI call (pinned H2D + forward + D2H) ----
-    for _ in range(2):
-        ctx.forward_host(hL.numpy(), hab.numpy(), hm.numpy(), 0.5, out_ab=hout.numpy())
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.forward_host(hL.numpy(), hab.numpy(), hm.numpy(), 0.5, out_ab=hout.numpy())
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
-    e2e = world * N * args.steps / e2e_s
+    e2e = None
+    if not args.skip_e2e:
+        for _ in range(2):
+            ctx.forward_host(hL.numpy(), hab.numpy(), hm.numpy(), 0.5, out_ab=hout.numpy())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.forward_host(hL.numpy(), hab.numpy(), hm.numpy(), 0.5, out_ab=hout.numpy())
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+        e2e = world * N * args.steps / e2e_s
 
     # ---- single-click latency (config 5): 20 sequential put_point -> net_forward, batch 1 ----
     lat = None
-    if rank == 0:
+    if rank == 0 and not args.skip_e2e:
         from interactive_deep_colorization_b200 import colorize_image as CI
         from interactive_deep_colorization_b200.engine import LhnContext
         lctx = LhnContext(device=local, max_n=1, H=X, W=X, dist=True)
@@ -238,7 +240,7 @@ def run_ours(args):
                         "tensor pipe is busy issued_mma_frac of peak"}
     # ---- CPU baseline (bounded sample, rank 0, N=1 only) ----
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.skip_e2e:
         ips, nimg, thr = cpu_baseline_run(synth.torch_state_dict(1234), 15.0, 64, os.cpu_count())
         cpu = {"value": ips, "unit": "images/s", "cores": thr, "kind": "port",
                "sample": "%d images @256x256, batch-1 loop of the CPU oracle port (torch fp32, %d threads, %d host cores)"
@@ -271,6 +273,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the e2e and latency legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

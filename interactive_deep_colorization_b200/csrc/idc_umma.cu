@@ -10,11 +10,18 @@
 // * 1e-3 ab parity needs ~22 mantissa bits: activations and weights are stored as
 //   FP16 hi + lo planes and every product is issued as 3 MMAs (hi*hi + hi*lo + lo*hi) into the
 //   same FP32 TMEM accumulator.  IDC_FLAG_FAST_FP16 drops the lo planes (1 MMA).
-// * warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2-5 = epilogue
-//   (TMEM -> regs -> bias/act/BN/global-hints -> hi/lo split -> NHWC store, or the fused
-//   model_out head).  Two TMEM accumulators: epilogue(i) overlaps mainloop(i+1).  Persistent
-//   grid = min(tiles, #SM).
+// * The tensor core's FP32 accumulator does not round to nearest: measured on B200 (round 1), a
+//   K=4608 layer accumulated entirely in TMEM (864 MMA steps) loses ~1e-5 relative per layer and the
+//   network ends at 1.2e-2 ab error although all three split terms are present.  So accumulation
+//   is CHUNKED: the tensor core only sums `chunk_kb` k-blocks (default 1 = 12 MMAs, the 8 small
+//   cross terms first) into a fresh TMEM buffer; the accumulate warps add each chunk into FP32
+//   REGISTERS with round-to-nearest CUDA-core adds while the next chunk runs (NBUF TMEM buffers).
+// * warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2-9 = accumulate +
+//   epilogue (TMEM chunk -> regs += ; at tile end bias/act/BN/global-hints -> hi/lo split -> NHWC
+//   store, or the fused model_out head).  Warp w owns TMEM lane quarter w%4 and column half (w-2)/4.
+//   Persistent grid = min(tiles, #SM).
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "idc_internal.h"
 
@@ -22,12 +29,14 @@ namespace idc {
 
 constexpr int kBM = 128;      // pixels per tile (UMMA M)
 constexpr int kBK = 64;       // channels per k-block (128 bytes of FP16 = one SW128 row)
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // 2 control warps + 8 accumulate/epilogue warps
+constexpr int kAccThreads = 256;
 
 struct UmmaParams {
   const CUtensorMap* amaps;  // device array, [view][hi, lo]
   const int4* kblk;          // [ncls][nkb] : {map index (hi), c0, dy, dx}
   int nkb, ncls;
+  int chunk_kb;              // k-blocks accumulated inside the tensor core per chunk (>=1)
   int n_img, tiles_y, tiles_x, n_tiles_n, total_tiles;
   int hbox, wbox, wshift;
   int Hl, Wl, cout_pad;
@@ -131,6 +140,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte-swizzled operand tile: rows of 64 FP16 (128 B), 8-row swizzle atoms 1024 B
@@ -159,11 +176,12 @@ struct SmemPlan {
   static constexpr int kABytes = kBM * kBK * 2;                 // 16 KB
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kBBytes);
-  static constexpr int kTail = 3 * BN * 4 + 272 * 4 + kMaxCls * 80 * 16 + 256;  // epi vecs, head, kblk, barriers
+  static constexpr int kTail = 3 * BN * 4 + 272 * 4 + kMaxCls * 80 * 16 + 256 + 128 * 2 * 4;  // epi vecs, head, kblk, barriers, head reduce
   static constexpr int kBudget = 232448 - 1024 - kTail;          // 227 KB opt-in limit minus alignment slack
   static constexpr int kStages = kBudget / kStageBytes >= 4 ? 4 : kBudget / kStageBytes;
   static constexpr int kTotal = kStages * kStageBytes + kTail + 1024;            // + alignment slack
-  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int kNBuf = (512 / BN) >= 4 ? 4 : (512 / BN);   // TMEM chunk buffers: 256->2, 192->2, 128->4, 64->4
+  static constexpr int kTmemCols = (kNBuf * BN <= 128) ? 128 : (kNBuf * BN <= 256 ? 256 : 512);
 };
 
 // ------------------------------------------------------------------------------------------
@@ -184,11 +202,13 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
   float* s_head = s_shift + BN;                                   // [2][128] + bias[2] (+pad)
   int4* s_kblk = reinterpret_cast<int4*>(s_head + 272);           // [ncls][nkb] (<= 4*80)
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_kblk + kMaxCls * 80);
-  uint64_t* full_bar = s_bar;
-  uint64_t* empty_bar = s_bar + STAGES;
-  uint64_t* tfull_bar = s_bar + 2 * STAGES;
-  uint64_t* tempty_bar = s_bar + 2 * STAGES + 2;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * STAGES + 4);
+  constexpr int NBUF = SP::kNBuf;
+  uint64_t* full_bar = s_bar;                      // [STAGES] TMA -> MMA
+  uint64_t* empty_bar = s_bar + STAGES;            // [STAGES] MMA -> TMA
+  uint64_t* tfull_bar = s_bar + 2 * STAGES;        // [NBUF]   MMA -> accumulate warps (chunk ready)
+  uint64_t* tempty_bar = s_bar + 2 * STAGES + NBUF;  // [NBUF] accumulate warps -> MMA (chunk drained)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * STAGES + 2 * NBUF);
+  float* s_red = reinterpret_cast<float*>(s_bar + 32);   // [128][2] fused-head partial sums, after the 256-byte barrier block
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -203,9 +223,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < NBUF; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), 4);
+      mbar_init(smem_u32(&tempty_bar[a]), 8);      // one arrive per accumulate warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -222,6 +242,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
 
   const int tiles_per_img = p.tiles_y * p.tiles_x;
   const int tiles_per_cls = p.n_img * tiles_per_img * p.n_tiles_n;
+  const int G = p.chunk_kb;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -260,47 +281,59 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       constexpr uint32_t idesc = make_idesc(BN);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err, 2);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int k = 0; k < p.nkb; ++k) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 3);
+      uint32_t cc = 0;                                   // chunk counter (persists across tiles)
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int k0 = 0; k0 < p.nkb; k0 += G, ++cc) {
+          const uint32_t buf = cc % NBUF;
+          const uint32_t bphase = (cc / NBUF) & 1;
+          mbar_wait(smem_u32(&tempty_bar[buf]), bphase ^ 1, p.err, 2);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * SP::kStageBytes);
-          const uint32_t sb = sa + (SPLIT ? 2 : 1) * SP::kABytes;
-          const uint64_t a_hi = make_sw128_desc(sa);
-          const uint64_t b_hi = make_sw128_desc(sb);
-#pragma unroll
-          for (int kk = 0; kk < kBK / 16; ++kk) {
-            const uint64_t adv = (uint64_t)(kk * 2);  // 16 FP16 = 32 bytes = 2 descriptor units
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          const int k1 = (k0 + G < p.nkb) ? k0 + G : p.nkb;
+          for (int k = k0; k < k1; ++k) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 3);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * SP::kStageBytes);
+            const uint32_t sb = sa + (SPLIT ? 2 : 1) * SP::kABytes;
+            const uint64_t a_hi = make_sw128_desc(sa);
+            const uint64_t b_hi = make_sw128_desc(sb);
+            uint32_t first = (k == k0) ? 0u : 1u;         // first MMA of a chunk overwrites the buffer
             if (SPLIT) {
               const uint64_t a_lo = make_sw128_desc(sa + SP::kABytes);
               const uint64_t b_lo = make_sw128_desc(sb + SP::kBBytes);
-              // small cross terms first, dominant term last
-              umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, (k | kk) ? 1u : 0u);
-              umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-              umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
-            } else {
-              umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, (k | kk) ? 1u : 0u);
+              // the 8 small cross terms first (accumulator still tiny -> their truncation is harmless),
+              // then the 4 dominant hi*hi terms
+#pragma unroll
+              for (int kk = 0; kk < kBK / 16; ++kk) {
+                const uint64_t adv = (uint64_t)(kk * 2);  // 16 FP16 = 32 bytes = 2 descriptor units
+                umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, first);
+                umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                first = 1u;
+              }
             }
+#pragma unroll
+            for (int kk = 0; kk < kBK / 16; ++kk) {
+              const uint64_t adv = (uint64_t)(kk * 2);
+              umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
+              first = 1u;
+            }
+            umma_commit(smem_u32(&empty_bar[stage]));   // frees the smem stage when these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem stage when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(smem_u32(&tfull_bar[buf]));        // chunk complete -> accumulate warps
         }
-        umma_commit(smem_u32(&tfull_bar[acc]));      // accumulator complete -> epilogue
       }
     }
   } else {
-    // =============================== epilogue (4 warps) ==========================
+    // ====================== accumulate + epilogue (8 warps) ======================
+    constexpr int CH = BN / 2;               // accumulator columns per thread
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;        // column half
     const int row = quarter * 32 + lane;     // pixel row of the tile
-    const int et = threadIdx.x - 64;         // 0..127
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    const int et = threadIdx.x - 64;         // 0..255
+    const int c_base = half * CH;
+    uint32_t cc = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int cls = tile / tiles_per_cls;
       int r = tile - cls * tiles_per_cls;
       const int nt = r % p.n_tiles_n;
@@ -311,62 +344,87 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       const int x = (r % p.tiles_x) * p.wbox + (row & (p.wbox - 1));
       const bool valid = y < p.Hl && x < p.Wl;
       const int n0 = nt * BN;
-      // stage this tile's per-channel epilogue vectors
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = et; i < BN; i += 128) {
+      // stage this tile's per-channel epilogue vectors (previous tile's readers are done: barrier)
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = et; i < BN; i += kAccThreads) {
         s_bias[i] = p.bias[n0 + i];
         s_scale[i] = p.scale[n0 + i];
         s_shift[i] = p.shift[n0 + i] + (p.gadd ? p.gadd[(size_t)img * p.gadd_ld + n0 + i] * p.gadd_mult : 0.f);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 4);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+      float acc[CH];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) acc[j] = 0.f;
+      for (int k0 = 0; k0 < p.nkb; k0 += G, ++cc) {
+        const uint32_t buf = cc % NBUF;
+        const uint32_t bphase = (cc / NBUF) & 1;
+        mbar_wait(smem_u32(&tfull_bar[buf]), bphase, p.err, 4);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + c_base;
+        if (CH >= 128) {     // 128 accumulators + a 32-wide load would spill: use 16-wide pieces
+#pragma unroll
+          for (int pc = 0; pc < CH / 16; ++pc) {
+            uint32_t v[16];
+            tmem_ld16(taddr + pc * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[pc * 16 + j] += __uint_as_float(v[j]);   // FP32 round-to-nearest
+          }
+        } else {
+#pragma unroll
+          for (int pc = 0; pc < CH / 32; ++pc) {
+            uint32_t v[32];
+            tmem_ld32(taddr + pc * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[pc * 32 + j] += __uint_as_float(v[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+      }
 
+      // ---- epilogue on the register accumulators ----
       size_t opix = 0;
       if (valid) {
-        if (p.out_f32) opix = ((size_t)(img * p.Hl + y) * p.Wl + x) * p.out_ld + n0;
-        else opix = ((size_t)(img * p.Hout + y * p.os + (cls >> 1)) * p.Wout + x * p.os + (cls & 1)) * p.Cout + n0;
+        if (p.out_f32) opix = ((size_t)(img * p.Hl + y) * p.Wl + x) * p.out_ld + n0 + c_base;
+        else opix = ((size_t)(img * p.Hout + y * p.os + (cls >> 1)) * p.Wout + x * p.os + (cls & 1)) * p.Cout + n0 + c_base;
       }
       float h0 = 0.f, h1 = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < BN; ch += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + ch, v);
-        tmem_ld_wait();
-        float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = __uint_as_float(v[j]) + s_bias[ch + j];
+      for (int ch = 0; ch < CH; ch += 16) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float t = acc[ch + j] + s_bias[c_base + ch + j];
           if (p.act == ACT_RELU) t = fmaxf(t, 0.f);
           else if (p.act == ACT_LEAKY02) t = t > 0.f ? t : 0.2f * t;
-          f[j] = fmaf(t, s_scale[ch + j], s_shift[ch + j]);
+          f[j] = fmaf(t, s_scale[c_base + ch + j], s_shift[c_base + ch + j]);
         }
         if (p.wout) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            h0 = fmaf(f[j], s_head[ch + j], h0);
-            h1 = fmaf(f[j], s_head[128 + ch + j], h1);
+          for (int j = 0; j < 16; ++j) {
+            h0 = fmaf(f[j], s_head[c_base + ch + j], h0);
+            h1 = fmaf(f[j], s_head[128 + c_base + ch + j], h1);
           }
         } else if (valid) {
           if (p.out_f32) {
             float4* o = reinterpret_cast<float4*>(p.out_f32 + opix + ch);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+            for (int q = 0; q < 4; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
           } else {
             uint4* oh = reinterpret_cast<uint4*>(p.out_hi + opix + ch);
             uint4* ol = SPLIT ? reinterpret_cast<uint4*>(p.out_lo + opix + ch) : nullptr;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 2; ++q) {
               __align__(16) __half hh[8];
               __align__(16) __half ll[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 if (SPLIT) split_h(f[q * 8 + j], hh[j], ll[j]);
-                else hh[j] = __float2half_rn(f[q * 8 + j]);
+                else hh[j] = __float2half_rn(fminf(fmaxf(f[q * 8 + j], -65504.f), 65504.f));
               }
               oh[q] = *reinterpret_cast<uint4*>(hh);
               if (SPLIT) ol[q] = *reinterpret_cast<uint4*>(ll);
@@ -374,16 +432,19 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           }
         }
       }
-      // release the accumulator
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
-      if (p.wout && valid) {
-        // model_out: conv1x1(128->2) + tanh, x110 (model.py:108-109,175)
-        const size_t HW = (size_t)p.Hl * p.Wl;
-        const size_t o = (size_t)img * 2 * HW + (size_t)y * p.Wl + x;
-        p.out_ab[o] = tanhf(h0 + s_head[256]) * 110.0f * p.out_mult;
-        p.out_ab[o + HW] = tanhf(h1 + s_head[257]) * 110.0f * p.out_mult;
+      if (p.wout) {
+        // model_out: conv1x1(128->2) + tanh, x110 (model.py:108-109,175); the two column halves of a
+        // pixel live in two warps -> combine through smem
+        if (half == 1) { s_red[row * 2] = h0; s_red[row * 2 + 1] = h1; }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (half == 0 && valid) {
+          h0 += s_red[row * 2];
+          h1 += s_red[row * 2 + 1];
+          const size_t HW = (size_t)p.Hl * p.Wl;
+          const size_t o = (size_t)img * 2 * HW + (size_t)y * p.Wl + x;
+          p.out_ab[o] = tanhf(h0 + s_head[256]) * 110.0f * p.out_mult;
+          p.out_ab[o + HW] = tanhf(h1 + s_head[257]) * 110.0f * p.out_mult;
+        }
       }
     }
   }
@@ -544,6 +605,13 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
 
   UmmaParams& q = pl->prm;
   q.amaps = pl->d_amaps; q.kblk = pl->d_kblk; q.nkb = nkb; q.ncls = op.ncls;
+  {
+    // chunk_kb: k-blocks summed inside the tensor core before the FP32 round-to-nearest add.
+    // 1 is the most accurate; the narrow BN=64 tiles drain too quickly to hide the hand-off, so 2 there.
+    int g = c->fast ? 4 : (op.bn_tile == 64 ? 2 : 1);
+    if (const char* e = getenv("IDC_CHUNK_KB")) { int v = atoi(e); if (v >= 1) g = v; }
+    q.chunk_kb = g;
+  }
   q.tiles_y = ceil_div(op.Hl, op.hbox); q.tiles_x = ceil_div(op.Wl, op.wbox);
   q.n_tiles_n = op.cout_pad / op.bn_tile;
   q.hbox = op.hbox; q.wbox = op.wbox;

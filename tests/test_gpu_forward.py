@@ -148,3 +148,29 @@ def test_full_size_batch_properties(synth_sd):
     ref = util.oracle_forward(synth_sd, L[[5, 40]], ab[[5, 40]], m[[5, 40]], 0.5)
     assert util.maxabs(out[[5, 40]], ref) <= TOL_AB
     ctx.close()
+
+
+def test_global_hints_branch(synth_sd):
+    """row a15: 4-layer global MLP + per-(image, channel) add on conv4_3 (Caffe spec; parity unpinned,
+    checked against oracle/caffe_spec.py + the glob_add path of oracle/lhn_ref.py)."""
+    from oracle import caffe_spec
+    gsd = caffe_spec.synthetic_glob_state_dict()
+    sd = dict(synth_sd)
+    sd.update({k: torch.from_numpy(v) for k, v in gsd.items()})
+    L, ab, m = util.small_batch(3, 64, seed=300)
+    glob_ab, sat = synth.synthetic_glob(3, seed=1)
+    glob = np.ascontiguousarray(np.concatenate([glob_ab, sat], axis=1).astype(np.float32))      # [3,316]
+    gvec = caffe_spec.global_hints_vector(gsd, glob)
+    ref, inter = util.oracle_forward(synth_sd, L, ab, m, 0.5, glob_add=gvec, intermediates=True)
+    ref_noglob = util.oracle_forward(synth_sd, L, ab, m, 0.5)
+    assert util.maxabs(ref, ref_noglob) > 0.5                      # the branch actually matters
+    for engine in ("simt", "tcgen05"):
+        ctx = util.make_ctx(sd, 64, 64, max_n=3, engine=engine, global_hints=True)
+        r = ctx.forward_device(util.dev(L), util.dev(ab), util.dev(m), 0.5, glob=util.dev(glob))
+        torch.cuda.synchronize()
+        assert util.maxabs(ctx.get_activation("conv4_3", 3), inter["conv4_3"]) < 2e-4, engine
+        assert util.maxabs(r["ab"], ref) <= TOL_AB, engine
+        r0 = ctx.forward_device(util.dev(L), util.dev(ab), util.dev(m), 0.5)          # glob omitted -> plain network
+        torch.cuda.synchronize()
+        assert util.maxabs(r0["ab"], ref_noglob) <= TOL_AB, engine
+        ctx.close()
