@@ -554,6 +554,9 @@ int idc_adopt_weights(idc_ctx* c) {
   CUDA_TRY(c, cudaSetDevice(c->dev));
   int rc = plan_engines(c);
   if (rc != IDC_OK) return rc;
+  // conv1_1 takes its weights as a kernel parameter: read them back from the (possibly received) arena
+  CUDA_TRY(c, cudaMemcpy(c->h_w11.w, c->w11, sizeof(c->h_w11.w), cudaMemcpyDeviceToHost));
+  CUDA_TRY(c, cudaMemcpy(c->h_w11.b, c->b11, sizeof(c->h_w11.b), cudaMemcpyDeviceToHost));
   c->raw.clear();
   c->weights_ready = true;
   if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }

@@ -20,54 +20,52 @@ __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
 }
 
 // ------------------------------------------------------------------------------------------
-// conv1_1: one thread per pixel, 64 output channels in registers, weights broadcast from smem
+// conv1_1: one thread per pixel, 64 output channels in registers.  The 36x64 weights travel as a
+// __grid_constant__ kernel parameter, so every FFMA takes its weight straight from the constant
+// bank (warp-uniform operand, no LDS/LDG in the inner loop): the first version read them from
+// shared memory and was LSU-bound at 1.6 ms per 64-image batch (round-1 profile).
 // ------------------------------------------------------------------------------------------
+// a / d for finite, normal-range a: reciprocal multiply + one FMA residual correction (the compiler's
+// own division sequence without its special-case slow path; inputs are bounded Lab values)
+__device__ __forceinline__ float div_corrected(float a, float d, float rd) {
+  const float q = a * rd;
+  return fmaf(fmaf(-q, d, a), rd, q);
+}
+
 template <bool SPLIT>
-__global__ void __launch_bounds__(128) conv1_1_kernel(const float* __restrict__ L, const float* __restrict__ ab,
-                                                      const float* __restrict__ mask, float maskcent,
-                                                      const float* __restrict__ w, const float* __restrict__ b,
-                                                      int N, int H, int W, float* __restrict__ outf,
-                                                      __half* __restrict__ ohi, __half* __restrict__ olo) {
-  __shared__ __align__(16) float ws[36 * 64];
-  __shared__ float bs[64];
-  for (int i = threadIdx.x; i < 36 * 64; i += blockDim.x) ws[i] = w[i];
-  if (threadIdx.x < 64) bs[threadIdx.x] = b[threadIdx.x];
-  __syncthreads();
-  const size_t HW = (size_t)H * W;
+__global__ void __launch_bounds__(128) conv1_1_kernel(const __grid_constant__ Conv11Weights W,
+                                                      const float* __restrict__ L, const float* __restrict__ ab,
+                                                      const float* __restrict__ mask, float maskcent, int N, int H,
+                                                      int Wd, float* __restrict__ outf, __half* __restrict__ ohi,
+                                                      __half* __restrict__ olo) {
+  const size_t HW = (size_t)H * Wd;
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= (size_t)N * HW) return;
   const int n = (int)(pix / HW);
   const int r = (int)(pix - (size_t)n * HW);
-  const int y = r / W, x = r - y * W;
+  const int y = r / Wd, x = r - y * Wd;
   float in[36];
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
       const int iy = y + ky - 1, ix = x + kx - 1;
-      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-      const size_t o = (size_t)iy * W + ix;
+      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < Wd;
+      const size_t o = (size_t)iy * Wd + ix;
       const int t = (ky * 3 + kx) * 4;
       // zero padding applies to the concatenated, normalised input (model.py:148 then Conv2d pad)
-      in[t + 0] = ok ? __ldg(L + (size_t)n * HW + o) / 100.0f : 0.f;
-      in[t + 1] = ok ? __ldg(ab + (size_t)n * 2 * HW + o) / 110.0f : 0.f;
-      in[t + 2] = ok ? __ldg(ab + (size_t)n * 2 * HW + HW + o) / 110.0f : 0.f;
+      in[t + 0] = ok ? div_corrected(__ldg(L + (size_t)n * HW + o), 100.0f, 0.01f) : 0.f;
+      in[t + 1] = ok ? div_corrected(__ldg(ab + (size_t)n * 2 * HW + o), 110.0f, 1.0f / 110.0f) : 0.f;
+      in[t + 2] = ok ? div_corrected(__ldg(ab + (size_t)n * 2 * HW + HW + o), 110.0f, 1.0f / 110.0f) : 0.f;
       in[t + 3] = ok ? (__ldg(mask + (size_t)n * HW + o) - maskcent) : 0.f;
     }
   float acc[64];
 #pragma unroll
-  for (int c = 0; c < 64; ++c) acc[c] = bs[c];
+  for (int c = 0; c < 64; ++c) acc[c] = W.b[c];
 #pragma unroll
   for (int k = 0; k < 36; ++k) {
-    const float a = in[k];
 #pragma unroll
-    for (int c4 = 0; c4 < 16; ++c4) {
-      const float4 wv = *reinterpret_cast<const float4*>(&ws[k * 64 + c4 * 4]);
-      acc[c4 * 4 + 0] = fmaf(a, wv.x, acc[c4 * 4 + 0]);
-      acc[c4 * 4 + 1] = fmaf(a, wv.y, acc[c4 * 4 + 1]);
-      acc[c4 * 4 + 2] = fmaf(a, wv.z, acc[c4 * 4 + 2]);
-      acc[c4 * 4 + 3] = fmaf(a, wv.w, acc[c4 * 4 + 3]);
-    }
+    for (int c = 0; c < 64; ++c) acc[c] = fmaf(in[k], W.w[k * 64 + c], acc[c]);
   }
 #pragma unroll
   for (int c = 0; c < 64; ++c) acc[c] = fmaxf(acc[c], 0.f);
@@ -96,10 +94,10 @@ cudaError_t launch_conv1_1(Ctx* c, int n, const float* L, const float* ab, const
   const size_t npix = (size_t)n * o.H * o.W;
   const int grid = (int)((npix + 127) / 128);
   if (c->simt)
-    conv1_1_kernel<false><<<grid, 128, 0, st>>>(L, ab, mask, maskcent, c->w11, c->b11, n, o.H, o.W,
+    conv1_1_kernel<false><<<grid, 128, 0, st>>>(c->h_w11, L, ab, mask, maskcent, n, o.H, o.W,
                                                 static_cast<float*>(o.p0), nullptr, nullptr);
   else
-    conv1_1_kernel<true><<<grid, 128, 0, st>>>(L, ab, mask, maskcent, c->w11, c->b11, n, o.H, o.W, nullptr,
+    conv1_1_kernel<true><<<grid, 128, 0, st>>>(c->h_w11, L, ab, mask, maskcent, n, o.H, o.W, nullptr,
                                                static_cast<__half*>(o.p0), static_cast<__half*>(o.p1));
   c->launch_count++;
   return cudaGetLastError();

@@ -96,6 +96,12 @@ struct ConvOp {
   double flops_per_image = 0;
 };
 
+// conv1_1 weights as a kernel parameter (constant bank): [36][64] with k = tap*4 + cin, then bias
+struct Conv11Weights {
+  float w[36 * 64];
+  float b[64];
+};
+
 struct HostTensor {
   std::vector<float> data;
   std::vector<int64_t> dims;
@@ -118,6 +124,7 @@ struct Ctx {
   // conv1_1 (4->64) + regression head + misc small weights (device fp32)
   float* w11 = nullptr;   // [36][64]  k = tap*4 + cin
   float* b11 = nullptr;   // [64]
+  Conv11Weights h_w11;    // host copy passed by value to conv1_1_kernel
   float* wout = nullptr;  // [2][128]
   float* bout = nullptr;  // [2]
   // global hints MLP (device fp32)

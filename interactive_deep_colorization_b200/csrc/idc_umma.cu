@@ -371,6 +371,15 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[pc * 16 + j] += __uint_as_float(v[j]);   // FP32 round-to-nearest
           }
+        } else if (CH == 64) {   // both loads in flight before the wait: hides one TMEM round trip per chunk
+          uint32_t v0[32], v1[32];
+          tmem_ld32(taddr, v0);
+          tmem_ld32(taddr + 32, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(v0[j]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[(32 + j) % CH] += __uint_as_float(v1[j]);
         } else {
 #pragma unroll
           for (int pc = 0; pc < CH / 32; ++pc) {
@@ -607,8 +616,9 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   q.amaps = pl->d_amaps; q.kblk = pl->d_kblk; q.nkb = nkb; q.ncls = op.ncls;
   {
     // chunk_kb: k-blocks summed inside the tensor core before the FP32 round-to-nearest add.
-    // 1 is the most accurate; the narrow BN=64 tiles drain too quickly to hide the hand-off, so 2 there.
-    int g = c->fast ? 4 : (op.bn_tile == 64 ? 2 : 1);
+    // 1 is the most accurate (1.5e-4 ab error end to end, 3.4e-4 with 2 everywhere -- profiles/);
+    // the BN<=128 tiles finish a k-block in <=768 cycles, too fast to hide the per-chunk hand-off: 2 there.
+    int g = c->fast ? 4 : (op.bn_tile <= 128 ? 2 : 1);
     if (const char* e = getenv("IDC_CHUNK_KB")) { int v = atoi(e); if (v >= 1) g = v; }
     q.chunk_kb = g;
   }
