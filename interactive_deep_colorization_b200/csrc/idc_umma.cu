@@ -171,27 +171,30 @@ __device__ __forceinline__ void split_h(float v, __half& hi, __half& lo) {
   lo = __float2half_rn(v - __half2float(hi));
 }
 
-template <int BN, bool SPLIT>
+template <int BN, int MT, bool SPLIT>
 struct SmemPlan {
-  static constexpr int kABytes = kBM * kBK * 2;                 // 16 KB
+  static constexpr int kABytes = MT * kBM * kBK * 2;            // MT M-tiles of 128 pixels x 64 ch FP16 (16 KB each)
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kBBytes);
   static constexpr int kTail = 3 * BN * 4 + 272 * 4 + kMaxCls * 80 * 16 + 256 + 128 * 2 * 4;  // epi vecs, head, kblk, barriers, head reduce
   static constexpr int kBudget = 232448 - 1024 - kTail;          // 227 KB opt-in limit minus alignment slack
   static constexpr int kStages = kBudget / kStageBytes >= 4 ? 4 : kBudget / kStageBytes;
   static constexpr int kTotal = kStages * kStageBytes + kTail + 1024;            // + alignment slack
-  static constexpr int kNBuf = (512 / BN) >= 4 ? 4 : (512 / BN);   // TMEM chunk buffers: 256->2, 192->2, 128->4, 64->4
-  static constexpr int kTmemCols = (kNBuf * BN <= 128) ? 128 : (kNBuf * BN <= 256 ? 256 : 512);
+  static constexpr int kBufCols = MT * BN;                       // TMEM columns of one chunk buffer
+  static constexpr int kNBuf = (512 / kBufCols) >= 4 ? 4 : (512 / kBufCols);
+  static constexpr int kTmemCols = (kNBuf * kBufCols <= 128) ? 128 : (kNBuf * kBufCols <= 256 ? 256 : 512);
+  static constexpr int kCH = (MT == 2) ? BN : BN / 2;            // accumulator columns per accumulate thread
+  static_assert(kStages >= 2, "need at least a double-buffered operand ring");
 };
 
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <int BN, bool SPLIT>
+template <int BN, int MT, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_constant__ CUtensorMap bmap_lo,
                  const UmmaParams p) {
-  using SP = SmemPlan<BN, SPLIT>;
+  using SP = SmemPlan<BN, MT, SPLIT>;
   constexpr int STAGES = SP::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -256,7 +259,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         r /= p.n_tiles_n;
         const int img = r / tiles_per_img;
         r -= img * tiles_per_img;
-        const int y0 = (r / p.tiles_x) * p.hbox, x0 = (r % p.tiles_x) * p.wbox;
+        const int y0 = (r / p.tiles_x) * (p.hbox * MT), x0 = (r % p.tiles_x) * p.wbox;
         const int brow = cls * p.cout_pad + nt * BN;
         const int4* kb = s_kblk + cls * p.nkb;
         for (int k = 0; k < p.nkb; ++k) {
@@ -288,34 +291,39 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           const uint32_t bphase = (cc / NBUF) & 1;
           mbar_wait(smem_u32(&tempty_bar[buf]), bphase ^ 1, p.err, 2);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * BN;
+          const uint32_t d_tmem = tmem_base + buf * SP::kBufCols;
           const int k1 = (k0 + G < p.nkb) ? k0 + G : p.nkb;
           for (int k = k0; k < k1; ++k) {
             mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 3);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * SP::kStageBytes);
             const uint32_t sb = sa + (SPLIT ? 2 : 1) * SP::kABytes;
-            const uint64_t a_hi = make_sw128_desc(sa);
             const uint64_t b_hi = make_sw128_desc(sb);
-            uint32_t first = (k == k0) ? 0u : 1u;         // first MMA of a chunk overwrites the buffer
-            if (SPLIT) {
-              const uint64_t a_lo = make_sw128_desc(sa + SP::kABytes);
-              const uint64_t b_lo = make_sw128_desc(sb + SP::kBBytes);
-              // the 8 small cross terms first (accumulator still tiny -> their truncation is harmless),
-              // then the 4 dominant hi*hi terms
+            const uint64_t b_lo = make_sw128_desc(sb + SP::kBBytes);
+            const uint32_t fresh = (k == k0) ? 0u : 1u;    // first MMA into a chunk buffer overwrites it
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint64_t a_hi = make_sw128_desc(sa + mt * (kBM * kBK * 2));
+              const uint64_t a_lo = make_sw128_desc(sa + SP::kABytes + mt * (kBM * kBK * 2));
+              const uint32_t d = d_tmem + mt * BN;
+              uint32_t first = fresh;
+              if (SPLIT) {
+                // the 8 small cross terms first (accumulator still tiny -> their truncation is harmless),
+                // then the 4 dominant hi*hi terms
+#pragma unroll
+                for (int kk = 0; kk < kBK / 16; ++kk) {
+                  const uint64_t adv = (uint64_t)(kk * 2);  // 16 FP16 = 32 bytes = 2 descriptor units
+                  umma_f16(d, a_lo + adv, b_hi + adv, idesc, first);
+                  umma_f16(d, a_hi + adv, b_lo + adv, idesc, 1u);
+                  first = 1u;
+                }
+              }
 #pragma unroll
               for (int kk = 0; kk < kBK / 16; ++kk) {
-                const uint64_t adv = (uint64_t)(kk * 2);  // 16 FP16 = 32 bytes = 2 descriptor units
-                umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, first);
-                umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                const uint64_t adv = (uint64_t)(kk * 2);
+                umma_f16(d, a_hi + adv, b_hi + adv, idesc, first);
                 first = 1u;
               }
-            }
-#pragma unroll
-            for (int kk = 0; kk < kBK / 16; ++kk) {
-              const uint64_t adv = (uint64_t)(kk * 2);
-              umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
-              first = 1u;
             }
             umma_commit(smem_u32(&empty_bar[stage]));   // frees the smem stage when these MMAs retire
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -326,12 +334,13 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
     }
   } else {
     // ====================== accumulate + epilogue (8 warps) ======================
-    constexpr int CH = BN / 2;               // accumulator columns per thread
+    constexpr int CH = SP::kCH;              // accumulator columns per thread
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;        // column half
+    const int half = (warp - 2) >> 2;        // MT==1: column half of the tile; MT==2: which M-tile
     const int row = quarter * 32 + lane;     // pixel row of the tile
     const int et = threadIdx.x - 64;         // 0..255
-    const int c_base = half * CH;
+    const int c_base = (MT == 2) ? 0 : half * CH;          // first output column of this thread
+    const int t_base = (MT == 2) ? half * BN : half * CH;   // its first TMEM column inside a chunk buffer
     uint32_t cc = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int cls = tile / tiles_per_cls;
@@ -340,7 +349,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       r /= p.n_tiles_n;
       const int img = r / tiles_per_img;
       r -= img * tiles_per_img;
-      const int y = (r / p.tiles_x) * p.hbox + (row >> p.wshift);
+      const int y = (r / p.tiles_x) * (p.hbox * MT) + (MT == 2 ? half * p.hbox : 0) + (row >> p.wshift);
       const int x = (r % p.tiles_x) * p.wbox + (row & (p.wbox - 1));
       const bool valid = y < p.Hl && x < p.Wl;
       const int n0 = nt * BN;
@@ -361,7 +370,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         const uint32_t bphase = (cc / NBUF) & 1;
         mbar_wait(smem_u32(&tfull_bar[buf]), bphase, p.err, 4);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + c_base;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * SP::kBufCols + t_base;
         if (CH >= 128) {     // 128 accumulators + a 32-wide load would spill: use 16-wide pieces
 #pragma unroll
           for (int pc = 0; pc < CH / 16; ++pc) {
@@ -444,11 +453,12 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       if (p.wout) {
         // model_out: conv1x1(128->2) + tanh, x110 (model.py:108-109,175); the two column halves of a
         // pixel live in two warps -> combine through smem
-        if (half == 1) { s_red[row * 2] = h0; s_red[row * 2 + 1] = h1; }
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (half == 0 && valid) {
-          h0 += s_red[row * 2];
-          h1 += s_red[row * 2 + 1];
+        if (MT == 1) {
+          if (half == 1) { s_red[row * 2] = h0; s_red[row * 2 + 1] = h1; }
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (half == 0) { h0 += s_red[row * 2]; h1 += s_red[row * 2 + 1]; }
+        }
+        if ((MT == 2 || half == 0) && valid) {
           const size_t HW = (size_t)p.Hl * p.Wl;
           const size_t o = (size_t)img * 2 * HW + (size_t)y * p.Wl + x;
           p.out_ab[o] = tanhf(h0 + s_head[256]) * 110.0f * p.out_mult;
@@ -493,6 +503,7 @@ struct UmmaPlan {
   CUtensorMap bmap_hi, bmap_lo;
   UmmaParams prm{};
   int num_sms = 148;
+  int mt = 1;               // M-tiles (128 pixels each) per CTA tile
 };
 
 struct ViewKey {
@@ -502,18 +513,18 @@ struct ViewKey {
 
 static int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
-template <int BN, bool SPLIT>
+template <int BN, int MT, bool SPLIT>
 static cudaError_t launch_inst(const UmmaPlan& pl, const UmmaParams& prm, cudaStream_t st) {
-  using SP = SmemPlan<BN, SPLIT>;
+  using SP = SmemPlan<BN, MT, SPLIT>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<BN, MT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SP::kTotal);
     if (e != cudaSuccess) return e;
     attr = true;
   }
   const int grid = prm.total_tiles < pl.num_sms ? prm.total_tiles : pl.num_sms;
-  umma_conv_kernel<BN, SPLIT><<<grid, kThreads, SP::kTotal, st>>>(pl.bmap_hi, pl.bmap_lo, prm);
+  umma_conv_kernel<BN, MT, SPLIT><<<grid, kThreads, SP::kTotal, st>>>(pl.bmap_hi, pl.bmap_lo, prm);
   return cudaGetLastError();
 }
 
@@ -535,6 +546,16 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
     const int t = ceil_div(op.Wl, wb) * ceil_div(op.Hl, hb);
     if (t < best) { best = t; op.wbox = wb; op.hbox = hb; }
   }
+  // Two M-tiles per CTA tile (one 256-pixel TMA box, two MMAs sharing each B tile) for the narrow-N layers:
+  // halves the weight re-streaming and the per-k-block hand-off overhead.  Only when the launch still
+  // fills the machine at the ctx's max batch (the batch-1 latency ctx keeps 128-pixel tiles).
+  pl->mt = 1;
+  if (op.bn_tile <= 128) {
+    const long tiles2 = (long)op.ncls * c->max_n * ceil_div(op.Hl, 2 * op.hbox) * ceil_div(op.Wl, op.wbox) *
+                        (op.cout_pad / op.bn_tile);
+    if (tiles2 >= 2L * pl->num_sms && op.hbox * 2 <= 256) pl->mt = 2;
+  }
+  if (const char* e = getenv("IDC_MT")) { int v = atoi(e); if (v == 1 || (v == 2 && op.bn_tile <= 128)) pl->mt = v; }
   // views + k-block table
   std::vector<ViewKey> views;
   const int nkb = op.K / kBK;
@@ -574,7 +595,7 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
       cuuint64_t dims[4] = {(cuuint64_t)b.C, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)c->max_n};
       cuuint64_t strides[3] = {(cuuint64_t)vk.s * b.C * 2, (cuuint64_t)vk.s * b.W * b.C * 2,
                                (cuuint64_t)b.H * b.W * b.C * 2};
-      cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)op.wbox, (cuuint32_t)op.hbox, 1};
+      cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)op.wbox, (cuuint32_t)(op.hbox * pl->mt), 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = enc(&amaps[i * 2 + part], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -618,11 +639,11 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
     // chunk_kb: k-blocks summed inside the tensor core before the FP32 round-to-nearest add.
     // 1 is the most accurate (1.5e-4 ab error end to end, 3.4e-4 with 2 everywhere -- profiles/);
     // the BN<=128 tiles finish a k-block in <=768 cycles, too fast to hide the per-chunk hand-off: 2 there.
-    int g = c->fast ? 4 : (op.bn_tile <= 128 ? 2 : 1);
+    int g = c->fast ? 4 : ((op.bn_tile <= 128 && pl->mt == 1) || op.bn_tile == 64 ? 2 : 1);
     if (const char* e = getenv("IDC_CHUNK_KB")) { int v = atoi(e); if (v >= 1) g = v; }
     q.chunk_kb = g;
   }
-  q.tiles_y = ceil_div(op.Hl, op.hbox); q.tiles_x = ceil_div(op.Wl, op.wbox);
+  q.tiles_y = ceil_div(op.Hl, op.hbox * pl->mt); q.tiles_x = ceil_div(op.Wl, op.wbox);
   q.n_tiles_n = op.cout_pad / op.bn_tile;
   q.hbox = op.hbox; q.wbox = op.wbox;
   q.wshift = 0;
@@ -664,13 +685,15 @@ cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float ou
   if (op.fuse_out_head && !out_ab_fused) return cudaErrorInvalidValue;
   c->launch_count++;
   const bool split = !c->fast;
-#define IDC_LAUNCH(BN_)                                                       \
-  return split ? launch_inst<BN_, true>(*pl, prm, st) : launch_inst<BN_, false>(*pl, prm, st)
-  switch (op.bn_tile) {
-    case 64: IDC_LAUNCH(64);
-    case 128: IDC_LAUNCH(128);
-    case 192: IDC_LAUNCH(192);
-    case 256: IDC_LAUNCH(256);
+#define IDC_LAUNCH(BN_, MT_)                                                   \
+  return split ? launch_inst<BN_, MT_, true>(*pl, prm, st) : launch_inst<BN_, MT_, false>(*pl, prm, st)
+  switch (op.bn_tile * 10 + pl->mt) {
+    case 641: IDC_LAUNCH(64, 1);
+    case 642: IDC_LAUNCH(64, 2);
+    case 1281: IDC_LAUNCH(128, 1);
+    case 1282: IDC_LAUNCH(128, 2);
+    case 1921: IDC_LAUNCH(192, 1);
+    case 2561: IDC_LAUNCH(256, 1);
     default: return cudaErrorInvalidValue;
   }
 #undef IDC_LAUNCH

@@ -10,11 +10,18 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def setup(synth_sd):
+@pytest.fixture(scope="module", params=[1, 2], ids=["mt1", "mt2"])
+def setup(request, synth_sd):
+    """mt = M-tiles per CTA tile (IDC_MT is read when the launch plan is built): both the 128-pixel
+    and the 256-pixel tile paths are exercised on every op that supports them."""
+    import os
     L, ab, m = util.small_batch(3, 64, seed=300)
     _, inter = util.oracle_forward(synth_sd, L, ab, m, 0.5, dist=False, intermediates=True)
-    ctx = util.make_ctx(synth_sd, 64, 64, max_n=3, engine="tcgen05", keep_conv10=True, use_graph=False)
+    os.environ["IDC_MT"] = str(request.param)
+    try:
+        ctx = util.make_ctx(synth_sd, 64, 64, max_n=3, engine="tcgen05", keep_conv10=True, use_graph=False)
+    finally:
+        del os.environ["IDC_MT"]
     yield ctx, inter
     ctx.close()
 
