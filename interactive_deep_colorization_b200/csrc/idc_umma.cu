@@ -342,6 +342,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
     const int c_base = (MT == 2) ? 0 : half * CH;          // first output column of this thread
     const int t_base = (MT == 2) ? half * BN : half * CH;   // its first TMEM column inside a chunk buffer
     uint32_t cc = 0;
+    int staged_key = -1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int cls = tile / tiles_per_cls;
       int r = tile - cls * tiles_per_cls;
@@ -353,14 +354,19 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       const int x = (r % p.tiles_x) * p.wbox + (row & (p.wbox - 1));
       const bool valid = y < p.Hl && x < p.Wl;
       const int n0 = nt * BN;
-      // stage this tile's per-channel epilogue vectors (previous tile's readers are done: barrier)
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int i = et; i < BN; i += kAccThreads) {
-        s_bias[i] = p.bias[n0 + i];
-        s_scale[i] = p.scale[n0 + i];
-        s_shift[i] = p.shift[n0 + i] + (p.gadd ? p.gadd[(size_t)img * p.gadd_ld + n0 + i] * p.gadd_mult : 0.f);
+      // stage this tile's per-channel epilogue vectors -- only when they change (n-tile, or image when a
+      // global-hints vector is added); for the single-n-tile layers that is once per kernel
+      const int vkey = p.gadd ? (img * p.n_tiles_n + nt) : nt;
+      if (vkey != staged_key) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // previous tile's readers are done
+        for (int i = et; i < BN; i += kAccThreads) {
+          s_bias[i] = p.bias[n0 + i];
+          s_scale[i] = p.scale[n0 + i];
+          s_shift[i] = p.shift[n0 + i] + (p.gadd ? p.gadd[(size_t)img * p.gadd_ld + n0 + i] * p.gadd_mult : 0.f);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        staged_key = vkey;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
 
       float acc[CH];
 #pragma unroll
@@ -457,6 +463,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           if (half == 1) { s_red[row * 2] = h0; s_red[row * 2 + 1] = h1; }
           asm volatile("bar.sync 2, 256;" ::: "memory");
           if (half == 0) { h0 += s_red[row * 2]; h1 += s_red[row * 2 + 1]; }
+          asm volatile("bar.sync 2, 256;" ::: "memory");     // s_red is rewritten by the next tile
         }
         if ((MT == 2 || half == 0) && valid) {
           const size_t HW = (size_t)p.Hl * p.Wl;
@@ -637,9 +644,11 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   q.amaps = pl->d_amaps; q.kblk = pl->d_kblk; q.nkb = nkb; q.ncls = op.ncls;
   {
     // chunk_kb: k-blocks summed inside the tensor core before the FP32 round-to-nearest add.
-    // 1 is the most accurate (1.5e-4 ab error end to end, 3.4e-4 with 2 everywhere -- profiles/);
-    // the BN<=128 tiles finish a k-block in <=768 cycles, too fast to hide the per-chunk hand-off: 2 there.
-    int g = c->fast ? 4 : ((op.bn_tile <= 128 && pl->mt == 1) || op.bn_tile == 64 ? 2 : 1);
+    // 1 is the most accurate (1.5e-4 ab error end to end, 3.4e-4 with 2 everywhere -- profiles/).
+    // Draining a chunk costs ~8 serial TMEM round trips (~1600 cycles for 128 columns per thread), about
+    // one k-block of MMA time at 256 output columns per CTA tile; the Cout<=128 layers have short K
+    // (few chunks per tile to amortise the tile epilogue), so they use 2 -> 2.1e-4 end to end.
+    int g = c->fast ? 4 : (op.bn_tile <= 128 ? 2 : 1);
     if (const char* e = getenv("IDC_CHUNK_KB")) { int v = atoi(e); if (v >= 1) g = v; }
     q.chunk_kb = g;
   }
