@@ -415,9 +415,17 @@ int alloc_workspace(Ctx* c) {
 
 int plan_engines(Ctx* c) {
   if (c->simt) return IDC_OK;
+  c->splitk_ws_floats = 0; c->splitk_max_tiles = 0;
   for (auto& op : c->ops) {
     int rc = umma_plan_op(c, op);
     if (rc != IDC_OK) return rc;
+  }
+  if (c->splitk_ws) { cudaFree(c->splitk_ws); c->splitk_ws = nullptr; }
+  if (c->splitk_counters) { cudaFree(c->splitk_counters); c->splitk_counters = nullptr; }
+  if (c->splitk_ws_floats) {
+    CUDA_TRY(c, cudaMalloc(&c->splitk_ws, c->splitk_ws_floats * sizeof(float)));
+    CUDA_TRY(c, cudaMalloc(&c->splitk_counters, sizeof(int) * (size_t)c->splitk_max_tiles));
+    CUDA_TRY(c, cudaMemset(c->splitk_counters, 0, sizeof(int) * (size_t)c->splitk_max_tiles));
   }
   return IDC_OK;
 }
@@ -776,6 +784,8 @@ int idc_destroy(idc_ctx* c) {
   for (auto& b : c->bufs) { if (b.p0) cudaFree(b.p0); if (b.p1) cudaFree(b.p1); }
   if (c->arena) cudaFree(c->arena);
   if (c->logits) cudaFree(c->logits);
+  if (c->splitk_ws) cudaFree(c->splitk_ws);
+  if (c->splitk_counters) cudaFree(c->splitk_counters);
   if (c->gvec) cudaFree(c->gvec);
   if (c->gtmp) cudaFree(c->gtmp);
   if (c->h_err) cudaFreeHost(c->h_err);

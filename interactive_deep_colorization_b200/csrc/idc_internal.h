@@ -137,6 +137,9 @@ struct Ctx {
   // workspace
   float* logits = nullptr;     // [max_n*(H/4)*(W/4)][cout_pad(529)]
   float* conv10_f32 = nullptr; // SIMT: conv10_2 is a normal buffer; unused otherwise
+  // split-K workspace of the tcgen05 engine (sized by umma_plan_op, allocated after planning)
+  float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;
+  int* splitk_counters = nullptr; int splitk_max_tiles = 0;
   int* d_err = nullptr;        // watchdog flag (mapped pinned host memory: survives a device trap)
   int* h_err = nullptr;
   // staging for idc_forward_host

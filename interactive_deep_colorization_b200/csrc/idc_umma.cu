@@ -37,6 +37,9 @@ struct UmmaParams {
   const int4* kblk;          // [ncls][nkb] : {map index (hi), c0, dy, dx}
   int nkb, ncls;
   int chunk_kb;              // k-blocks accumulated inside the tensor core per chunk (>=1)
+  int split_k;               // >1: K is split over `split_k` CTAs per tile (small-batch latency path)
+  float* ws;                 // split-K partial sums [work item][128 rows][MT*BN] FP32
+  int* counters;             // split-K arrival counters [tile] (self-resetting)
   int n_img, tiles_y, tiles_x, n_tiles_n, total_tiles;
   int hbox, wbox, wshift;
   int Hl, Wl, cout_pad;
@@ -211,6 +214,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
   uint64_t* tfull_bar = s_bar + 2 * STAGES;        // [NBUF]   MMA -> accumulate warps (chunk ready)
   uint64_t* tempty_bar = s_bar + 2 * STAGES + NBUF;  // [NBUF] accumulate warps -> MMA (chunk drained)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * STAGES + 2 * NBUF);
+  int* s_flag = reinterpret_cast<int*>(s_bar + 31);        // split-K 'last arriver' flag
   float* s_red = reinterpret_cast<float*>(s_bar + 32);   // [128][2] fused-head partial sums, after the 256-byte barrier block
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -244,25 +248,30 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
   const uint32_t tmem_base = *s_tmem;
 
   const int tiles_per_img = p.tiles_y * p.tiles_x;
-  const int tiles_per_cls = p.n_img * tiles_per_img * p.n_tiles_n;
   const int G = p.chunk_kb;
+  const int S = p.split_k;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int cls = tile / tiles_per_cls;
-        int r = tile - cls * tiles_per_cls;
+      for (int w = blockIdx.x; w < p.total_tiles * S; w += gridDim.x) {
+        const int tile = w / S, ks = w - tile * S;
+        const int kbeg = (ks * p.nkb) / S, kend = ((ks + 1) * p.nkb) / S;
+        // tile order: n-tile fastest, then output-parity class, then spatial tile, then image -- CTAs that
+        // run together share the A tile (all n-tiles) and the source rows (all 4 classes of an up-layer)
+        int r = tile;
         const int nt = r % p.n_tiles_n;
         r /= p.n_tiles_n;
+        const int cls = r % p.ncls;
+        r /= p.ncls;
         const int img = r / tiles_per_img;
         r -= img * tiles_per_img;
         const int y0 = (r / p.tiles_x) * (p.hbox * MT), x0 = (r % p.tiles_x) * p.wbox;
         const int brow = cls * p.cout_pad + nt * BN;
         const int4* kb = s_kblk + cls * p.nkb;
-        for (int k = 0; k < p.nkb; ++k) {
+        for (int k = kbeg; k < kend; ++k) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, SP::kStageBytes);
@@ -285,14 +294,16 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       uint32_t cc = 0;                                   // chunk counter (persists across tiles)
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        for (int k0 = 0; k0 < p.nkb; k0 += G, ++cc) {
+      for (int w = blockIdx.x; w < p.total_tiles * S; w += gridDim.x) {
+        const int ks = w % S;
+        const int kbeg = (ks * p.nkb) / S, kend = ((ks + 1) * p.nkb) / S;
+        for (int k0 = kbeg; k0 < kend; k0 += G, ++cc) {
           const uint32_t buf = cc % NBUF;
           const uint32_t bphase = (cc / NBUF) & 1;
           mbar_wait(smem_u32(&tempty_bar[buf]), bphase ^ 1, p.err, 2);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * SP::kBufCols;
-          const int k1 = (k0 + G < p.nkb) ? k0 + G : p.nkb;
+          const int k1 = (k0 + G < kend) ? k0 + G : kend;
           for (int k = k0; k < k1; ++k) {
             mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 3);
             tc_fence_after();
@@ -343,11 +354,14 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
     const int t_base = (MT == 2) ? half * BN : half * CH;   // its first TMEM column inside a chunk buffer
     uint32_t cc = 0;
     int staged_key = -1;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int cls = tile / tiles_per_cls;
-      int r = tile - cls * tiles_per_cls;
+    for (int w = blockIdx.x; w < p.total_tiles * S; w += gridDim.x) {
+      const int tile = w / S, ks = w - tile * S;
+      const int kbeg = (ks * p.nkb) / S, kend = ((ks + 1) * p.nkb) / S;
+      int r = tile;
       const int nt = r % p.n_tiles_n;
       r /= p.n_tiles_n;
+      const int cls = r % p.ncls;
+      r /= p.ncls;
       const int img = r / tiles_per_img;
       r -= img * tiles_per_img;
       const int y = (r / p.tiles_x) * (p.hbox * MT) + (MT == 2 ? half * p.hbox : 0) + (row >> p.wshift);
@@ -371,7 +385,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       float acc[CH];
 #pragma unroll
       for (int j = 0; j < CH; ++j) acc[j] = 0.f;
-      for (int k0 = 0; k0 < p.nkb; k0 += G, ++cc) {
+      for (int k0 = kbeg; k0 < kend; k0 += G, ++cc) {
         const uint32_t buf = cc % NBUF;
         const uint32_t bphase = (cc / NBUF) & 1;
         mbar_wait(smem_u32(&tfull_bar[buf]), bphase, p.err, 4);
@@ -410,6 +424,39 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
       }
 
+      // ---- split-K: park the partial tile in the workspace; the last CTA to arrive sums all slices in
+      //      fixed order (deterministic) and runs the epilogue ----
+      bool do_epi = true;
+      if (S > 1) {
+        float* wp = p.ws + ((size_t)w * kBM + row) * (MT * BN) + t_base;
+#pragma unroll
+        for (int j = 0; j < CH; j += 4)
+          __stcg(reinterpret_cast<float4*>(wp + j), make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+          const int old = atomicAdd(&p.counters[tile], 1);
+          const int last = (old == S - 1) ? 1 : 0;
+          if (last) p.counters[tile] = 0;              // all slices have arrived: reset for the next launch
+          *s_flag = last;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        do_epi = *s_flag != 0;
+        if (do_epi) {
+          __threadfence();
+#pragma unroll
+          for (int j = 0; j < CH; ++j) acc[j] = 0.f;
+          for (int q = 0; q < S; ++q) {
+            const float* rp = p.ws + ((size_t)(tile * S + q) * kBM + row) * (MT * BN) + t_base;
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(rp + j));
+              acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
+            }
+          }
+        }
+      }
+      if (do_epi) {
       // ---- epilogue on the register accumulators ----
       size_t opix = 0;
       if (valid) {
@@ -472,6 +519,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           p.out_ab[o + HW] = tanhf(h1 + s_head[257]) * 110.0f * p.out_mult;
         }
       }
+      }  // do_epi
     }
   }
 
@@ -511,6 +559,9 @@ struct UmmaPlan {
   UmmaParams prm{};
   int num_sms = 148;
   int mt = 1;               // M-tiles (128 pixels each) per CTA tile
+  int split_k = 1;
+  size_t ws_floats = 0;
+  int ws_tiles = 0;
 };
 
 struct ViewKey {
@@ -530,7 +581,8 @@ static cudaError_t launch_inst(const UmmaPlan& pl, const UmmaParams& prm, cudaSt
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  const int grid = prm.total_tiles < pl.num_sms ? prm.total_tiles : pl.num_sms;
+  const long items = (long)prm.total_tiles * prm.split_k;
+  const int grid = items < pl.num_sms ? (int)items : pl.num_sms;
   umma_conv_kernel<BN, MT, SPLIT><<<grid, kThreads, SP::kTotal, st>>>(pl.bmap_hi, pl.bmap_lo, prm);
   return cudaGetLastError();
 }
@@ -670,6 +722,23 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   }
   if (op.fuse_out_head) { q.wout = c->wout; q.bout = c->bout; }
   q.err = c->d_err;
+  // split-K for launches that cannot fill the machine even at the ctx's max batch (interactive path)
+  {
+    const long T = (long)op.ncls * c->max_n * q.tiles_y * q.tiles_x * q.n_tiles_n;
+    int S = 1;
+    if (T * 2 <= pl->num_sms && nkb >= 8 && !op.fuse_out_head && pl->mt == 1) {
+      S = (int)(pl->num_sms / T);
+      if (S > nkb / 4) S = nkb / 4;
+      if (S > 16) S = 16;
+      if (S < 1) S = 1;
+    }
+    if (const char* e = getenv("IDC_SPLIT_K")) { int v = atoi(e); if (v >= 1 && v <= nkb && pl->mt == 1) S = v; }
+    pl->split_k = S;
+    pl->ws_tiles = (int)T;
+    pl->ws_floats = S > 1 ? (size_t)T * S * kBM * op.bn_tile : 0;
+    if (pl->ws_floats > c->splitk_ws_floats) c->splitk_ws_floats = pl->ws_floats;
+    if (S > 1 && pl->ws_tiles > c->splitk_max_tiles) c->splitk_max_tiles = pl->ws_tiles;
+  }
   return IDC_OK;
 }
 
@@ -690,6 +759,10 @@ cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float ou
   prm.total_tiles = op.ncls * n * prm.tiles_y * prm.tiles_x * prm.n_tiles_n;
   prm.gadd = (op.epi.gadd && c->gadd_active) ? c->gvec : nullptr;
   prm.out_ab = out_ab_fused;
+  prm.split_k = pl->split_k;
+  prm.ws = c->splitk_ws;
+  prm.counters = c->splitk_counters;
+  if (pl->split_k > 1 && (!prm.ws || !prm.counters)) return cudaErrorInvalidValue;
   prm.out_mult = out_mult;
   if (op.fuse_out_head && !out_ab_fused) return cudaErrorInvalidValue;
   c->launch_count++;
