@@ -213,6 +213,7 @@ def run_ours(args):
         from interactive_deep_colorization_b200.engine import LhnContext
         lctx = LhnContext(device=local, max_n=1, H=X, W=X, dist=True)
         lctx.load_state_dict(synth.torch_state_dict(1234))
+        lctx.set_dist_resident(True)      # config 5: the click only needs dist[:, h//4, w//4]
         rs = np.random.RandomState(0)
         l1 = np.ascontiguousarray(L[:1]); a1 = np.zeros((1, 2, X, X), np.float32); m1 = np.zeros((1, 1, X, X), np.float32)
         times = []
@@ -220,12 +221,13 @@ def run_ours(args):
             loc = rs.randint(8, X - 8, 2)
             CI.put_point(a1[0], m1[0], loc, 3, rs.uniform(-80, 80, 2))
             t = time.perf_counter()
-            lctx.forward_host(l1, a1, m1, 0.5, want_dist=True, want_rgb=True)
+            lctx.forward_host(l1, a1, m1, 0.5, want_rgb=True)
+            lctx.fetch_dist(0, int(loc[0]) // 4, int(loc[1]) // 4)
             times.append((time.perf_counter() - t) * 1e3)
         times = times[5:]
         lat = {"p50_ms": float(np.percentile(times, 50)), "p99_ms": float(np.percentile(times, 99)),
-               "calls": len(times), "what": "C-ABI idc_forward_host, batch 1, dist head + Lab->RGB on, CUDA graph, "
-                                            "incl. H2D of L/hints and D2H of ab/dist/rgb"}
+               "calls": len(times), "what": "BASELINE config 5: put_point -> C-ABI idc_forward_host (batch 1, dist head + Lab->RGB on, "
+                                            "CUDA graph, H2D of L/hints, D2H of ab + rgb) + idc_fetch_dist of the clicked pixel"}
         lctx.close()
 
     if rank != 0:

@@ -110,6 +110,14 @@ int idc_forward_host(idc_ctx* ctx, int n, int h, int w, const float* L_mc, const
                      const float* mask, float maskcent, const float* glob, float* out_ab,
                      float* out_dist, uint8_t* out_rgb);
 
+/* Interactive path: keep the 529-bin distribution of the last idc_forward_host on the device instead
+ * of copying all of it back (8.7 MB at 256^2) -- the reference only ever reads one pixel of it per click
+ * (`self.dist_ab[:, h, w]`, data/colorize_image.py:329).  With resident mode on, idc_forward_host runs the
+ * dist head even when out_dist is NULL; idc_fetch_dist then copies dist[img, :, y4, x4] (529 floats) to
+ * host memory, or the whole [529, h/4, w/4] plane when y4 < 0. */
+int idc_set_dist_resident(idc_ctx* ctx, int on);
+int idc_fetch_dist(idc_ctx* ctx, int img, int y4, int x4, float* out_host);
+
 /* Stand-alone post-process: lab2rgb_transpose (data/colorize_image.py:20-28).
  * L [n,1,h,w] in [0,100] (NOT mean-centred), ab [n,2,h,w] -> rgb [n,h,w,3] uint8. DEVICE ptrs. */
 int idc_lab2rgb_u8(int device, int n, int h, int w, const float* L, const float* ab,

@@ -32,6 +32,8 @@ SYMBOLS = [
     ("idc_adopt_weights", _c.c_int, [_P]),
     ("idc_forward", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _c.c_float, _P, _P, _P, _P, _P]),
     ("idc_forward_host", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _c.c_float, _P, _P, _P, _P]),
+    ("idc_set_dist_resident", _c.c_int, [_P, _c.c_int]),
+    ("idc_fetch_dist", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P]),
     ("idc_lab2rgb_u8", _c.c_int, [_c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     ("idc_get_activation", _c.c_int, [_P, _c.c_char_p, _P, _c.c_size_t, _c.POINTER(_c.c_int),
                                       _c.POINTER(_c.c_int), _c.POINTER(_c.c_int)]),

@@ -213,22 +213,32 @@ class ColorizeImageB200(ColorizeImageBase):
 
 
 class _LazyUpsampledDist(object):
-    """[529, X, X] view of the [529, X/4, X/4] distribution: the reference materialises the
-    nearest x4 upsample (139 MB at 256^2, model.py:160); consumers only index it
-    (`dist_ab[:, h, w]`, data/colorize_image.py:329), so we replicate on read."""
+    """[529, X, X] view of the [529, X/4, X/4] distribution.  The reference materialises the nearest x4
+    upsample (139 MB at 256^2, model.py:160) and copies it to the host; its consumers only index single
+    pixels (`dist_ab[:, h, w]`, data/colorize_image.py:329).  Here the distribution stays on the device
+    (`fetch` pulls 529 floats per lookup) or is a host [529, X/4, X/4] array; either way it is
+    replicated on read."""
 
-    def __init__(self, d64):
-        self.d64 = d64
-        self.shape = (d64.shape[0], d64.shape[1] * 4, d64.shape[2] * 4)
-        self.dtype = d64.dtype
+    def __init__(self, d64=None, fetch=None, shape64=None):
+        self.d64, self._fetch = d64, fetch
+        s = d64.shape if d64 is not None else shape64
+        self.shape = (s[0], s[1] * 4, s[2] * 4)
+        self.dtype = np.dtype(np.float32)
+
+    def _plane(self):
+        if self.d64 is None:
+            self.d64 = self._fetch(None, None)
+        return self.d64
 
     def __getitem__(self, idx):
         if isinstance(idx, tuple) and len(idx) == 3 and all(isinstance(i, (int, np.integer)) for i in idx[1:]):
+            if self.d64 is None:
+                return self._fetch(int(idx[1]) // 4, int(idx[2]) // 4)[idx[0]]
             return self.d64[idx[0], idx[1] // 4, idx[2] // 4]
         return self.__array__()[idx]
 
     def __array__(self, dtype=None, copy=None):
-        a = np.repeat(np.repeat(self.d64, 4, axis=1), 4, axis=2)
+        a = np.repeat(np.repeat(self._plane(), 4, axis=1), 4, axis=2)
         return a.astype(dtype) if dtype is not None else a
 
 
@@ -257,16 +267,21 @@ class ColorizeImageB200Dist(ColorizeImageB200):
         B = np.ascontiguousarray(self.input_ab_mc, dtype=np.float32)[None]
         M = np.ascontiguousarray(self.input_mask_mult, dtype=np.float32)[None]
         ctx = self.net._context(A.shape[-2], A.shape[-1], 1)
-        r = ctx.forward_host(A, B, M, float(self.mask_cent), want_dist=True)
+        if self.materialize_full:
+            r = ctx.forward_host(A, B, M, float(self.mask_cent), want_dist=True)
+            self.dist_ab_64 = r["dist"][0]                   # [529, X/4, X/4]
+        else:
+            ctx.set_dist_resident(True)                      # dist stays in HBM; pixels are fetched on demand
+            r = ctx.forward_host(A, B, M, float(self.mask_cent))
         self.output_ab_raw = r["ab"][0]
-        self.dist_ab_64 = r["dist"][0]                       # [529, X/4, X/4]
         if self.materialize_full:
             self.dist_ab = np.repeat(np.repeat(self.dist_ab_64, 4, axis=1), 4, axis=2)
             self.dist_ab_full = np.zeros((self.AB, self.Xd, self.Xd))
             self.dist_ab_full[self.in_hull, :, :] = self.dist_ab
             self.dist_ab_grid = self.dist_ab_full.reshape((self.A, self.B, self.Xd, self.Xd))
         else:
-            self.dist_ab = _LazyUpsampledDist(self.dist_ab_64)
+            self.dist_ab = _LazyUpsampledDist(fetch=lambda y4, x4: ctx.fetch_dist(0, y4, x4),
+                                              shape64=(529, A.shape[-2] // 4, A.shape[-1] // 4))
         self.dist_ab_set = True
         # reference returns the regression output scaled by 110 twice (model.py:166-168, q1)
         return self.output_ab_raw * 110.0

@@ -424,8 +424,8 @@ int plan_engines(Ctx* c) {
   if (c->splitk_counters) { cudaFree(c->splitk_counters); c->splitk_counters = nullptr; }
   if (c->splitk_ws_floats) {
     CUDA_TRY(c, cudaMalloc(&c->splitk_ws, c->splitk_ws_floats * sizeof(float)));
-    CUDA_TRY(c, cudaMalloc(&c->splitk_counters, sizeof(int) * (size_t)c->splitk_max_tiles));
-    CUDA_TRY(c, cudaMemset(c->splitk_counters, 0, sizeof(int) * (size_t)c->splitk_max_tiles));
+    CUDA_TRY(c, cudaMalloc(&c->splitk_counters, sizeof(int) * 2 * (size_t)c->splitk_max_tiles));
+    CUDA_TRY(c, cudaMemset(c->splitk_counters, 0, sizeof(int) * 2 * (size_t)c->splitk_max_tiles));
   }
   return IDC_OK;
 }
@@ -629,7 +629,9 @@ int idc_forward_host(idc_ctx* c, int n, int h, int w, const float* L, const floa
   if (glob) CUDA_TRY(c, h2d(dglob, glob, (size_t)n * 316, (size_t)c->max_n * 4 * HW));
 
   const bool use_graph = !(c->flags & IDC_FLAG_NO_GRAPH) && n <= 4;
-  const bool want_dist = out_dist != nullptr, want_rgb = out_rgb != nullptr, want_glob = glob != nullptr;
+  const bool copy_dist = out_dist != nullptr;
+  const bool want_dist = copy_dist || (c->dist_resident && c->dist);
+  const bool want_rgb = out_rgb != nullptr, want_glob = glob != nullptr;
   if (use_graph) {
     const void* key[8] = {(void*)(size_t)n, (void*)(size_t)want_dist, (void*)(size_t)want_rgb, (void*)(size_t)want_glob,
                           nullptr, nullptr, nullptr, nullptr};
@@ -663,14 +665,41 @@ int idc_forward_host(idc_ctx* c, int n, int h, int w, const float* L, const floa
     return cudaMemcpyAsync(stage, d, bytes, cudaMemcpyDeviceToHost, st);
   };
   CUDA_TRY(c, d2h(out_ab, dout, n * 2 * HW * sizeof(float), c->h_out));
-  if (want_dist) CUDA_TRY(c, d2h(out_dist, ddist, n * 529 * HW4 * sizeof(float), c->h_out + (size_t)c->max_n * 2 * HW));
+  if (copy_dist) CUDA_TRY(c, d2h(out_dist, ddist, n * 529 * HW4 * sizeof(float), c->h_out + (size_t)c->max_n * 2 * HW));
   if (want_rgb) CUDA_TRY(c, d2h(out_rgb, c->d_rgb, n * HW * 3, c->h_rgb));
   CUDA_TRY(c, cudaStreamSynchronize(st));
   if (!is_pinned(out_ab)) memcpy(out_ab, c->h_out, n * 2 * HW * sizeof(float));
-  if (want_dist && !is_pinned(out_dist)) memcpy(out_dist, c->h_out + (size_t)c->max_n * 2 * HW, n * 529 * HW4 * sizeof(float));
+  if (copy_dist && !is_pinned(out_dist)) memcpy(out_dist, c->h_out + (size_t)c->max_n * 2 * HW, n * 529 * HW4 * sizeof(float));
+  c->dist_valid_n = want_dist ? n : 0;
   if (want_rgb && !is_pinned(out_rgb)) memcpy(out_rgb, c->h_rgb, n * HW * 3);
   const int werr = *(volatile int*)c->h_err;
   if (werr) return fail(c, IDC_ERR_WATCHDOG, "device pipeline watchdog fired (code %d)", werr);
+  return IDC_OK;
+}
+
+int idc_set_dist_resident(idc_ctx* c, int on) {
+  if (!c) return IDC_ERR_ARG;
+  if (on && !c->dist) return fail(c, IDC_ERR_ARG, "resident dist requires IDC_FLAG_DIST");
+  c->dist_resident = on != 0;
+  return IDC_OK;
+}
+
+int idc_fetch_dist(idc_ctx* c, int img, int y4, int x4, float* out) {
+  if (!c || !out) return IDC_ERR_ARG;
+  if (img < 0 || img >= c->dist_valid_n || !c->d_out)
+    return fail(c, IDC_ERR_STATE, "no resident distribution for image %d (run idc_forward_host with resident mode on)", img);
+  const int H4 = c->H / 4, W4 = c->W / 4;
+  const size_t HW = (size_t)c->H * c->W, HW4 = (size_t)H4 * W4;
+  const float* d = c->d_out + (size_t)c->max_n * 2 * HW + (size_t)img * 529 * HW4;
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  if (y4 < 0) {
+    CUDA_TRY(c, cudaMemcpy(out, d, 529 * HW4 * sizeof(float), cudaMemcpyDeviceToHost));
+    return IDC_OK;
+  }
+  if (y4 >= H4 || x4 < 0 || x4 >= W4) return fail(c, IDC_ERR_ARG, "pixel (%d,%d) outside the %dx%d grid", y4, x4, H4, W4);
+  // one float per bin, bins are HW4 floats apart (NCHW)
+  CUDA_TRY(c, cudaMemcpy2D(out, sizeof(float), d + (size_t)y4 * W4 + x4, HW4 * sizeof(float), sizeof(float), 529,
+                           cudaMemcpyDeviceToHost));
   return IDC_OK;
 }
 

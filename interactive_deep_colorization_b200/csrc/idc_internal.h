@@ -156,6 +156,8 @@ struct Ctx {
   int graph_launches = 0;
   bool gadd_active = false;     // a global-hints vector was supplied to this forward
   int last_n = 0;
+  bool dist_resident = false;   // keep the dist of the last forward_host on the device (idc_fetch_dist)
+  int dist_valid_n = 0;
   // per-op profiling
   bool profiling = false;
   std::vector<std::vector<cudaEvent_t>> prof_runs;   // one event list per profiled forward

@@ -214,7 +214,6 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
   uint64_t* tfull_bar = s_bar + 2 * STAGES;        // [NBUF]   MMA -> accumulate warps (chunk ready)
   uint64_t* tempty_bar = s_bar + 2 * STAGES + NBUF;  // [NBUF] accumulate warps -> MMA (chunk drained)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * STAGES + 2 * NBUF);
-  int* s_flag = reinterpret_cast<int*>(s_bar + 31);        // split-K 'last arriver' flag
   float* s_red = reinterpret_cast<float*>(s_bar + 32);   // [128][2] fused-head partial sums, after the 256-byte barrier block
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -424,39 +423,46 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
       }
 
-      // ---- split-K: park the partial tile in the workspace; the last CTA to arrive sums all slices in
-      //      fixed order (deterministic) and runs the epilogue ----
-      bool do_epi = true;
+      // ---- split-K: park the partial tile in the workspace, wait until all S slices of this tile have
+      //      arrived (they are co-resident: work items <= #SMs by construction), then every CTA reduces and
+      //      finishes ITS share of the 16-column pieces (piece % S == ks), summing the slices in fixed order
+      //      (deterministic).  Arrive/depart counters reset themselves for the next launch / graph replay. ----
       if (S > 1) {
-        float* wp = p.ws + ((size_t)w * kBM + row) * (MT * BN) + t_base;
+        // workspace layout [work item][column quad][row] (float4): lanes = rows -> 512-byte coalesced
+        float4* wp = reinterpret_cast<float4*>(p.ws) + ((size_t)w * (MT * BN / 4) + t_base / 4) * kBM + row;
 #pragma unroll
         for (int j = 0; j < CH; j += 4)
-          __stcg(reinterpret_cast<float4*>(wp + j), make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+          __stcg(wp + (size_t)(j / 4) * kBM, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
         __threadfence();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
-          const int old = atomicAdd(&p.counters[tile], 1);
-          const int last = (old == S - 1) ? 1 : 0;
-          if (last) p.counters[tile] = 0;              // all slices have arrived: reset for the next launch
-          *s_flag = last;
+          int* cnt = p.counters + 2 * tile;
+          atomicAdd(cnt, 1);
+          const long long t0 = clock64();
+          int seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+            if (seen < S && clock64() - t0 > 6000000000LL) mbar_timeout(p.err, 5);
+          } while (seen < S);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        do_epi = *s_flag != 0;
-        if (do_epi) {
-          __threadfence();
 #pragma unroll
-          for (int j = 0; j < CH; ++j) acc[j] = 0.f;
+        for (int ch = 0; ch < CH; ch += 16) {
+          if (((c_base + ch) >> 4) % S != ks) continue;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[ch + j] = 0.f;
           for (int q = 0; q < S; ++q) {
-            const float* rp = p.ws + ((size_t)(tile * S + q) * kBM + row) * (MT * BN) + t_base;
+            const float4* rp = reinterpret_cast<const float4*>(p.ws) +
+                               ((size_t)(tile * S + q) * (MT * BN / 4) + (t_base + ch) / 4) * kBM + row;
 #pragma unroll
-            for (int j = 0; j < CH; j += 4) {
-              const float4 v = __ldcg(reinterpret_cast<const float4*>(rp + j));
-              acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
+            for (int j = 0; j < 16; j += 4) {
+              const float4 v = __ldcg(rp + (size_t)(j / 4) * kBM);
+              acc[ch + j] += v.x; acc[ch + j + 1] += v.y; acc[ch + j + 2] += v.z; acc[ch + j + 3] += v.w;
             }
           }
         }
       }
-      if (do_epi) {
+      {
       // ---- epilogue on the register accumulators ----
       size_t opix = 0;
       if (valid) {
@@ -466,6 +472,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       float h0 = 0.f, h1 = 0.f;
 #pragma unroll
       for (int ch = 0; ch < CH; ch += 16) {
+        if (S > 1 && ((c_base + ch) >> 4) % S != ks) continue;   // another CTA of the split finishes this piece
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -519,7 +526,14 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           p.out_ab[o + HW] = tanhf(h1 + s_head[257]) * 110.0f * p.out_mult;
         }
       }
-      }  // do_epi
+      }
+      if (S > 1) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // all of this CTA's workspace reads are done
+        if (et == 0) {
+          int* cnt = p.counters + 2 * tile;
+          if (atomicAdd(cnt + 1, 1) == S - 1) { cnt[0] = 0; cnt[1] = 0; __threadfence(); }
+        }
+      }
     }
   }
 
@@ -729,10 +743,13 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
     if (T * 2 <= pl->num_sms && nkb >= 8 && !op.fuse_out_head && pl->mt == 1) {
       S = (int)(pl->num_sms / T);
       if (S > nkb / 4) S = nkb / 4;
-      if (S > 16) S = 16;
+      if (S > op.bn_tile / 16) S = op.bn_tile / 16;      // one 16-column piece per CTA at least
       if (S < 1) S = 1;
     }
-    if (const char* e = getenv("IDC_SPLIT_K")) { int v = atoi(e); if (v >= 1 && v <= nkb && pl->mt == 1) S = v; }
+    if (const char* e = getenv("IDC_SPLIT_K")) {           // experiments; must keep all work items co-resident
+      int v = atoi(e);
+      if (v >= 1 && v <= nkb && v <= op.bn_tile / 16 && pl->mt == 1 && T * v <= pl->num_sms) S = v;
+    }
     pl->split_k = S;
     pl->ws_tiles = (int)T;
     pl->ws_floats = S > 1 ? (size_t)T * S * kBM * op.bn_tile : 0;

@@ -122,6 +122,20 @@ class LhnContext(object):
         _lib.check(self.h, rc)
         return {"ab": out_ab, "dist": out_dist if want_dist else None, "rgb": out_rgb if want_rgb else None}
 
+    def set_dist_resident(self, on=True):
+        """Interactive mode: the dist head runs on every forward_host but stays on the device."""
+        _lib.check(self.h, self.lib.idc_set_dist_resident(self.h, 1 if on else 0))
+
+    def fetch_dist(self, img=0, y4=None, x4=None):
+        """dist[img, :, y4, x4] (529 floats), or the whole [529, H/4, W/4] plane when y4 is None."""
+        if y4 is None:
+            out = np.empty((529, self.H // 4, self.W // 4), np.float32)
+            _lib.check(self.h, self.lib.idc_fetch_dist(self.h, img, -1, 0, _np_ptr(out)))
+        else:
+            out = np.empty((529,), np.float32)
+            _lib.check(self.h, self.lib.idc_fetch_dist(self.h, img, int(y4), int(x4), _np_ptr(out)))
+        return out
+
     # ---- introspection (tests) -------------------------------------------------------------
     def op_names(self):
         return [self.lib.idc_op_name(self.h, i).decode() for i in range(self.lib.idc_num_ops(self.h))]

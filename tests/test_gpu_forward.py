@@ -121,6 +121,11 @@ def test_wrapper_api_end_to_end(synth_sd):
     ret = cd.net_forward(a5, m5)
     gd = util.golden("lhn_dist_256.npz")
     assert util.maxabs(ret, gd["ret_quirk"]) < 0.15
+    # the distribution stays on the device; single pixels are fetched on demand (529 floats)
+    assert util.maxabs(np.asarray(cd.dist_ab[:, 64, 96]), gd["dist_rows"][:, 2, 3]) < 1e-5
+    assert util.maxabs(np.asarray(cd.dist_ab[:, 67, 99]), gd["dist_rows"][:, 2, 3]) < 1e-5     # nearest x4 upsample
+    full = np.asarray(cd.dist_ab)
+    assert full.shape == (529, 256, 256) and util.maxabs(full[:, ::32, ::32], gd["dist_rows"]) < 1e-5
     np.random.seed(0)
     reccs = cd.get_ab_reccs(128, 128, K=9, N=25000)
     assert reccs.shape == (9, 2) and np.all(np.abs(reccs) <= 110)
