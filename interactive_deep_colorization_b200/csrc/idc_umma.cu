@@ -103,6 +103,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
   }
 }
 
+// one lane of a converged warp (warp-uniform control flow keeps descriptors / addresses in uniform
+// registers; a role wrapped in `if (lane == 0)` makes ptxas re-broadcast every operand per instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -252,7 +264,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < p.total_tiles * S; w += gridDim.x) {
@@ -272,23 +284,26 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         const int4* kb = s_kblk + cls * p.nkb;
         for (int k = kbeg; k < kend; ++k) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 1);
-          const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_expect_tx(fb, SP::kStageBytes);
-          const int4 e = kb[k];
-          const uint32_t sa = smem_u32(smem + stage * SP::kStageBytes);
-          const CUtensorMap* am = p.amaps + e.x;
-          tma_load_4d(sa, am, fb, e.y, x0 + e.w, y0 + e.z, img);
-          if (SPLIT) tma_load_4d(sa + SP::kABytes, am + 1, fb, e.y, x0 + e.w, y0 + e.z, img);
-          const uint32_t sb = sa + (SPLIT ? 2 : 1) * SP::kABytes;
-          tma_load_2d(sb, &bmap_hi, fb, k * kBK, brow);
-          if (SPLIT) tma_load_2d(sb + SP::kBBytes, &bmap_lo, fb, k * kBK, brow);
+          if (elect_one()) {
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_expect_tx(fb, SP::kStageBytes);
+            const int4 e = kb[k];
+            const uint32_t sa = smem_u32(smem + stage * SP::kStageBytes);
+            const CUtensorMap* am = p.amaps + e.x;
+            tma_load_4d(sa, am, fb, e.y, x0 + e.w, y0 + e.z, img);
+            if (SPLIT) tma_load_4d(sa + SP::kABytes, am + 1, fb, e.y, x0 + e.w, y0 + e.z, img);
+            const uint32_t sb = sa + (SPLIT ? 2 : 1) * SP::kABytes;
+            tma_load_2d(sb, &bmap_hi, fb, k * kBK, brow);
+            if (SPLIT) tma_load_2d(sb + SP::kBBytes, &bmap_lo, fb, k * kBK, brow);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc(BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -306,6 +321,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           for (int k = k0; k < k1; ++k) {
             mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 3);
             tc_fence_after();
+            if (elect_one()) {
             const uint32_t sa = smem_u32(smem + stage * SP::kStageBytes);
             const uint32_t sb = sa + (SPLIT ? 2 : 1) * SP::kABytes;
             const uint64_t b_hi = make_sw128_desc(sb);
@@ -336,9 +352,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
               }
             }
             umma_commit(smem_u32(&empty_bar[stage]));   // frees the smem stage when these MMAs retire
+            if (k == k1 - 1) umma_commit(smem_u32(&tfull_bar[buf]));   // chunk complete -> accumulate warps
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(smem_u32(&tfull_bar[buf]));        // chunk complete -> accumulate warps
         }
       }
     }
