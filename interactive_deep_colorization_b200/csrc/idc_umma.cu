@@ -29,7 +29,9 @@ namespace idc {
 
 constexpr int kBM = 128;      // pixels per tile (UMMA M)
 constexpr int kBK = 64;       // channels per k-block (128 bytes of FP16 = one SW128 row)
-constexpr int kThreads = 320;   // 2 control warps + 8 accumulate/epilogue warps
+constexpr int kThreads = 384;   // control warpgroup (TMA, MMA, 2 idle warps) + 2 accumulate/epilogue warpgroups
+constexpr int kCtrlRegs = 40;    // setmaxnreg budgets: the control warpgroup gives its registers to the accumulate warps
+constexpr int kAccRegs = 232;
 constexpr int kAccThreads = 256;
 
 struct UmmaParams {
@@ -262,6 +264,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
   const int G = p.chunk_kb;
   const int S = p.split_k;
 
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
   if (warp == 0) {
     // =============================== TMA producer ===============================
     {
@@ -360,13 +363,14 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         }
       }
     }
-  } else {
+  } else if (warp >= 4) {
     // ====================== accumulate + epilogue (8 warps) ======================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kAccRegs));
     constexpr int CH = SP::kCH;              // accumulator columns per thread
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;        // MT==1: column half of the tile; MT==2: which M-tile
+    const int half = (warp - 4) >> 2;        // MT==1: column half of the tile; MT==2: which M-tile
     const int row = quarter * 32 + lane;     // pixel row of the tile
-    const int et = threadIdx.x - 64;         // 0..255
+    const int et = threadIdx.x - 128;        // 0..255
     const int c_base = (MT == 2) ? 0 : half * CH;          // first output column of this thread
     const int t_base = (MT == 2) ? half * BN : half * CH;   // its first TMEM column inside a chunk buffer
     uint32_t cc = 0;
@@ -408,14 +412,17 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         mbar_wait(smem_u32(&tfull_bar[buf]), bphase, p.err, 4);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * SP::kBufCols + t_base;
-        if (CH >= 128) {     // 128 accumulators + a 32-wide load would spill: use 16-wide pieces
+        if (CH >= 128) {     // 64 columns in flight per TMEM round trip (232-register budget after setmaxnreg)
 #pragma unroll
-          for (int pc = 0; pc < CH / 16; ++pc) {
-            uint32_t v[16];
-            tmem_ld16(taddr + pc * 16, v);
+          for (int pc = 0; pc < CH / 64; ++pc) {
+            uint32_t v0[32], v1[32];
+            tmem_ld32(taddr + pc * 64, v0);
+            tmem_ld32(taddr + pc * 64 + 32, v1);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[pc * 16 + j] += __uint_as_float(v[j]);   // FP32 round-to-nearest
+            for (int j = 0; j < 32; ++j) acc[pc * 64 + j] += __uint_as_float(v0[j]);   // FP32 round-to-nearest
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[pc * 64 + 32 + j] += __uint_as_float(v1[j]);
           }
         } else if (CH == 64) {   // both loads in flight before the wait: hides one TMEM round trip per chunk
           uint32_t v0[32], v1[32];
