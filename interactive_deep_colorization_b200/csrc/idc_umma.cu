@@ -55,6 +55,7 @@ struct UmmaParams {
   __half* out_hi;
   __half* out_lo;
   int Hout, Wout, Cout, os;
+  int omap;            // index into amaps of the output (TMA store) maps [cls][hi, lo], or -1: direct stores
   float* out_f32;      // logits [M][out_ld] or null
   int out_ld;
   const float* wout;   // fused head weights [2][128] or null
@@ -62,6 +63,7 @@ struct UmmaParams {
   float* out_ab;
   float out_mult;
   int* err;
+  int dbg;             // experiments only (IDC_DEBUG_SKIP): 1 = skip activation stores, 2 = skip the whole epilogue
 };
 
 // ------------------------------------------------------------------------------------------
@@ -131,6 +133,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
       : "memory");
 }
 
+// TMA store of a staged [hbox x wbox pixels][16 ch] slab (32-byte rows, SWIZZLE_32B); out-of-range pixels
+// of partial tiles are clipped by the hardware
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tmap), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(
@@ -194,9 +211,10 @@ struct SmemPlan {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kBBytes);
   static constexpr int kTail = 3 * BN * 4 + 272 * 4 + kMaxCls * 80 * 16 + 256 + 128 * 2 * 4;  // epi vecs, head, kblk, barriers, head reduce
-  static constexpr int kBudget = 232448 - 1024 - kTail;          // 227 KB opt-in limit minus alignment slack
+  static constexpr int kOutStage = 16384;                         // epilogue staging for TMA stores: 2 halves x (hi 4 KB + lo 4 KB)
+  static constexpr int kBudget = 232448 - 1024 - kTail - kOutStage;  // 227 KB opt-in limit minus alignment slack
   static constexpr int kStages = kBudget / kStageBytes >= 4 ? 4 : kBudget / kStageBytes;
-  static constexpr int kTotal = kStages * kStageBytes + kTail + 1024;            // + alignment slack
+  static constexpr int kTotal = kStages * kStageBytes + kOutStage + kTail + 1024;   // + alignment slack
   static constexpr int kBufCols = MT * BN;                       // TMEM columns of one chunk buffer
   static constexpr int kNBuf = (512 / kBufCols) >= 4 ? 4 : (512 / kBufCols);
   static constexpr int kTmemCols = (kNBuf * kBufCols <= 128) ? 128 : (kNBuf * kBufCols <= 256 ? 256 : 512);
@@ -215,7 +233,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
   constexpr int STAGES = SP::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* tail = smem + STAGES * SP::kStageBytes;
+  uint8_t* s_out = smem + STAGES * SP::kStageBytes;              // 1024-aligned (stage sizes are multiples of 1 KB)
+  uint8_t* tail = s_out + SP::kOutStage;
   float* s_bias = reinterpret_cast<float*>(tail);
   float* s_scale = s_bias + BN;
   float* s_shift = s_scale + BN;
@@ -385,6 +404,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       r /= p.ncls;
       const int img = r / tiles_per_img;
       r -= img * tiles_per_img;
+      const int r2 = r;
       const int y = (r / p.tiles_x) * (p.hbox * MT) + (MT == 2 ? half * p.hbox : 0) + (row >> p.wshift);
       const int x = (r % p.tiles_x) * p.wbox + (row & (p.wbox - 1));
       const bool valid = y < p.Hl && x < p.Wl;
@@ -487,7 +507,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           }
         }
       }
-      {
+      if (!(p.dbg & 2)) {
       // ---- epilogue on the register accumulators ----
       size_t opix = 0;
       if (valid) {
@@ -500,19 +520,28 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         if (S > 1 && ((c_base + ch) >> 4) % S != ks) continue;   // another CTA of the split finishes this piece
         float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float t = acc[ch + j] + s_bias[c_base + ch + j];
-          if (p.act == ACT_RELU) t = fmaxf(t, 0.f);
-          else if (p.act == ACT_LEAKY02) t = t > 0.f ? t : 0.2f * t;
-          f[j] = fmaf(t, s_scale[c_base + ch + j], s_shift[c_base + ch + j]);
+        for (int j4 = 0; j4 < 16; j4 += 4) {      // warp-uniform float4 reads of the staged per-channel vectors
+          const float4 vb = *reinterpret_cast<const float4*>(s_bias + c_base + ch + j4);
+          const float4 vs = *reinterpret_cast<const float4*>(s_scale + c_base + ch + j4);
+          const float4 vt = *reinterpret_cast<const float4*>(s_shift + c_base + ch + j4);
+          const float b4[4] = {vb.x, vb.y, vb.z, vb.w}, s4[4] = {vs.x, vs.y, vs.z, vs.w}, t4[4] = {vt.x, vt.y, vt.z, vt.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float t = acc[ch + j4 + j] + b4[j];
+            if (p.act == ACT_RELU) t = fmaxf(t, 0.f);
+            else if (p.act == ACT_LEAKY02) t = t > 0.f ? t : 0.2f * t;
+            f[j4 + j] = fmaf(t, s4[j], t4[j]);
+          }
         }
         if (p.wout) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            h0 = fmaf(f[j], s_head[c_base + ch + j], h0);
-            h1 = fmaf(f[j], s_head[128 + c_base + ch + j], h1);
+          for (int j4 = 0; j4 < 16; j4 += 4) {
+            const float4 w0 = *reinterpret_cast<const float4*>(s_head + c_base + ch + j4);
+            const float4 w1 = *reinterpret_cast<const float4*>(s_head + 128 + c_base + ch + j4);
+            h0 = fmaf(f[j4], w0.x, fmaf(f[j4 + 1], w0.y, fmaf(f[j4 + 2], w0.z, fmaf(f[j4 + 3], w0.w, h0))));
+            h1 = fmaf(f[j4], w1.x, fmaf(f[j4 + 1], w1.y, fmaf(f[j4 + 2], w1.z, fmaf(f[j4 + 3], w1.w, h1))));
           }
-        } else if (valid) {
+        } else if (valid && !(p.dbg & 1) && (p.out_f32 || p.omap < 0)) {
           if (p.out_f32) {
             float4* o = reinterpret_cast<float4*>(p.out_f32 + opix + ch);
 #pragma unroll
@@ -532,6 +561,40 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
               oh[q] = *reinterpret_cast<uint4*>(hh);
               if (SPLIT) ol[q] = *reinterpret_cast<uint4*>(ll);
             }
+          }
+        } else if (p.omap >= 0 && !(p.dbg & 1)) {
+          // ---- staged TMA store: this half's 128 pixel rows x 16 channels go to smem (32-byte rows,
+          //      SWIZZLE_32B so the 16-byte writes are bank-conflict free) and one elected thread hands the
+          //      slab to the TMA engine.  A 16-byte store per lane straight to global costs one L1
+          //      transaction per LANE (~38k cycles per 128x256 tile, measured); this costs ~0.5k. ----
+          __align__(16) __half hh[16];
+          __align__(16) __half ll[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (SPLIT) split_h(f[j], hh[j], ll[j]);
+            else hh[j] = __float2half_rn(fminf(fmaxf(f[j], -65504.f), 65504.f));
+          }
+          const uint32_t sbuf = smem_u32(s_out) + half * 8192;
+          const bool issuer = (threadIdx.x & 127) == 0;
+          if (issuer) bulk_wait_read0();                        // previous slab has left the staging buffer
+          asm volatile("bar.sync %0, 128;" ::"r"(3 + half) : "memory");
+          const uint32_t sw = (row >> 2) & 1;                   // Swizzle<1,4,3>: 16-byte chunk ^= byte-offset bit 7
+          const uint32_t r0 = sbuf + row * 32;
+          st_shared_v4(r0 + ((0 ^ sw) << 4), *reinterpret_cast<uint4*>(&hh[0]));
+          st_shared_v4(r0 + ((1 ^ sw) << 4), *reinterpret_cast<uint4*>(&hh[8]));
+          if (SPLIT) {
+            st_shared_v4(r0 + 4096 + ((0 ^ sw) << 4), *reinterpret_cast<uint4*>(&ll[0]));
+            st_shared_v4(r0 + 4096 + ((1 ^ sw) << 4), *reinterpret_cast<uint4*>(&ll[8]));
+          }
+          fence_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(3 + half) : "memory");
+          if (issuer) {
+            const CUtensorMap* om = p.amaps + p.omap + cls * 2;
+            const int ty0 = (r2 / p.tiles_x) * (p.hbox * MT) + (MT == 2 ? half * p.hbox : 0);
+            const int tx0 = (r2 % p.tiles_x) * p.wbox;
+            tma_store_4d(om, sbuf, n0 + c_base + ch, tx0, ty0, img);
+            if (SPLIT) tma_store_4d(om + 1, sbuf + 4096, n0 + c_base + ch, tx0, ty0, img);
+            bulk_commit();
           }
         }
       }
@@ -563,6 +626,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
   }
 
   // ---- teardown ----
+  if (warp >= 4 && (threadIdx.x & 127) == 0) bulk_wait_all();   // staged TMA stores have left shared memory
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -723,6 +787,38 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
       return IDC_ERR_CUDA;
     }
   }
+  // output (TMA store) maps: one [hi, lo] pair per output-parity class, 16-channel slabs, SWIZZLE_32B
+  int omap_index = -1;
+  if (op.out_buf >= 0 && !op.out_f32 && !op.fuse_out_head) {
+    omap_index = (int)amaps.size();
+    const ActBuf& ob = c->bufs[op.out_buf];
+    for (int cls = 0; cls < op.ncls; ++cls) {
+      const int cy = op.os == 2 ? (cls >> 1) : 0, cx = op.os == 2 ? (cls & 1) : 0;
+      const int Hv = (ob.H - cy + op.os - 1) / op.os, Wv = (ob.W - cx + op.os - 1) / op.os;
+      for (int part = 0; part < 2; ++part) {
+        CUtensorMap m;
+        char* base = (char*)(part == 0 ? ob.p0 : ob.p1);
+        if (!base) { amaps.push_back(amaps.back()); continue; }    // fast mode: lo unused
+        base += ((size_t)cy * ob.W + cx) * ob.C * sizeof(__half);
+        cuuint64_t dims[4] = {(cuuint64_t)ob.C, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)c->max_n};
+        cuuint64_t strides[3] = {(cuuint64_t)op.os * ob.C * 2, (cuuint64_t)op.os * ob.W * ob.C * 2,
+                                 (cuuint64_t)ob.H * ob.W * ob.C * 2};
+        cuuint32_t box[4] = {16, (cuuint32_t)op.wbox, (cuuint32_t)op.hbox, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+          char msg[256];
+          snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled(out) failed (%d) for op %s", (int)r, op.name.c_str());
+          c->err = msg;
+          return IDC_ERR_CUDA;
+        }
+        amaps.push_back(m);
+      }
+    }
+  }
+  if (const char* e = getenv("IDC_DIRECT_STORES")) { if (atoi(e)) omap_index = -1; }
   if (cudaMalloc(&pl->d_amaps, amaps.size() * sizeof(CUtensorMap)) != cudaSuccess ||
       cudaMalloc(&pl->d_kblk, kblk.size() * sizeof(int4)) != cudaSuccess) {
     c->err = "cudaMalloc failed in umma_plan_op";
@@ -760,7 +856,10 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
     q.Hout = ob.H; q.Wout = ob.W; q.Cout = ob.C; q.os = op.os;
   }
   if (op.fuse_out_head) { q.wout = c->wout; q.bout = c->bout; }
+  q.omap = omap_index;
   q.err = c->d_err;
+  q.dbg = 0;
+  if (const char* e = getenv("IDC_DEBUG_SKIP")) q.dbg = atoi(e);
   // split-K for launches that cannot fill the machine even at the ctx's max batch (interactive path)
   {
     const long T = (long)op.ncls * c->max_n * q.tiles_y * q.tiles_x * q.n_tiles_n;
