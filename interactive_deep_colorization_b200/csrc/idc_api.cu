@@ -787,6 +787,22 @@ double idc_op_flops(idc_ctx* c, int i) {
   return (c && i >= 0 && i < (int)c->ops.size()) ? c->ops[i].flops_per_image : 0.0;
 }
 
+// experiments (tools/): per-CTA cycle counters of the LAST tcgen05 launch; out[148*8] long long
+extern "C" int idc_debug_counters(idc_ctx* c, int enable, long long* out_host) {
+  if (!c) return IDC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  if (enable && !c->dbgbuf) {
+    CUDA_TRY(c, cudaMalloc(&c->dbgbuf, 256 * 8 * sizeof(long long)));
+    CUDA_TRY(c, cudaMemset(c->dbgbuf, 0, 256 * 8 * sizeof(long long)));
+  }
+  if (out_host && c->dbgbuf) {
+    CUDA_TRY(c, cudaDeviceSynchronize());
+    CUDA_TRY(c, cudaMemcpy(out_host, c->dbgbuf, 148 * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  if (!enable && c->dbgbuf) { cudaFree(c->dbgbuf); c->dbgbuf = nullptr; }
+  return IDC_OK;
+}
+
 int idc_num_ops(idc_ctx* c) { return c ? (int)c->ops.size() : 0; }
 const char* idc_op_name(idc_ctx* c, int i) {
   return (c && i >= 0 && i < (int)c->ops.size()) ? c->ops[i].name.c_str() : nullptr;

@@ -140,6 +140,7 @@ struct Ctx {
   // split-K workspace of the tcgen05 engine (sized by umma_plan_op, allocated after planning)
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;
   int* splitk_counters = nullptr; int splitk_max_tiles = 0;
+  long long* dbgbuf = nullptr;   // experiments: per-CTA cycle counters of the last tcgen05 launch
   int* d_err = nullptr;        // watchdog flag (mapped pinned host memory: survives a device trap)
   int* h_err = nullptr;
   // staging for idc_forward_host

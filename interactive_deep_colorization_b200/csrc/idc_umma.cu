@@ -30,8 +30,8 @@ namespace idc {
 constexpr int kBM = 128;      // pixels per tile (UMMA M)
 constexpr int kBK = 64;       // channels per k-block (128 bytes of FP16 = one SW128 row)
 constexpr int kThreads = 384;   // control warpgroup (TMA, MMA, 2 idle warps) + 2 accumulate/epilogue warpgroups
-constexpr int kCtrlRegs = 40;    // setmaxnreg budgets: the control warpgroup gives its registers to the accumulate warps
-constexpr int kAccRegs = 232;
+constexpr int kCtrlRegs = 56;    // setmaxnreg budgets: the control warpgroup gives its registers to the accumulate warps
+constexpr int kAccRegs = 224;
 constexpr int kAccThreads = 256;
 
 struct UmmaParams {
@@ -55,7 +55,7 @@ struct UmmaParams {
   __half* out_hi;
   __half* out_lo;
   int Hout, Wout, Cout, os;
-  int omap;            // index into amaps of the output (TMA store) maps [cls][hi, lo], or -1: direct stores
+  int store_mode;      // 0 = every lane stores its own row; 1 = warp-transposed through smem (default)
   float* out_f32;      // logits [M][out_ld] or null
   int out_ld;
   const float* wout;   // fused head weights [2][128] or null
@@ -63,6 +63,7 @@ struct UmmaParams {
   float* out_ab;
   float out_mult;
   int* err;
+  long long* dbgbuf;   // experiments only: per-CTA cycle counters [grid][8]
   int dbg;             // experiments only (IDC_DEBUG_SKIP): 1 = skip activation stores, 2 = skip the whole epilogue
 };
 
@@ -281,6 +282,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
 
   const int tiles_per_img = p.tiles_y * p.tiles_x;
   const int G = p.chunk_kb;
+  long long t_wait_tfull_g = 0, t_drain_g = 0, t_epi_g = 0;
   const int S = p.split_k;
 
   if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
@@ -330,18 +332,24 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       uint32_t cc = 0;                                   // chunk counter (persists across tiles)
+      long long t_wait_tempty = 0, t_wait_full = 0;
+      const long long t_start = clock64();
       for (int w = blockIdx.x; w < p.total_tiles * S; w += gridDim.x) {
         const int ks = w % S;
         const int kbeg = (ks * p.nkb) / S, kend = ((ks + 1) * p.nkb) / S;
         for (int k0 = kbeg; k0 < kend; k0 += G, ++cc) {
           const uint32_t buf = cc % NBUF;
           const uint32_t bphase = (cc / NBUF) & 1;
+          const long long tA = p.dbgbuf ? clock64() : 0;
           mbar_wait(smem_u32(&tempty_bar[buf]), bphase ^ 1, p.err, 2);
+          if (p.dbgbuf) t_wait_tempty += clock64() - tA;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * SP::kBufCols;
           const int k1 = (k0 + G < kend) ? k0 + G : kend;
           for (int k = k0; k < k1; ++k) {
+            const long long tB = p.dbgbuf ? clock64() : 0;
             mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 3);
+            if (p.dbgbuf) t_wait_full += clock64() - tB;
             tc_fence_after();
             if (elect_one()) {
             const uint32_t sa = smem_u32(smem + stage * SP::kStageBytes);
@@ -381,6 +389,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           }
         }
       }
+      if (p.dbgbuf && lane == 0) {
+        p.dbgbuf[blockIdx.x * 8 + 0] = clock64() - t_start;
+        p.dbgbuf[blockIdx.x * 8 + 1] = t_wait_tempty;
+        p.dbgbuf[blockIdx.x * 8 + 2] = t_wait_full;
+      }
     }
   } else if (warp >= 4) {
     // ====================== accumulate + epilogue (8 warps) ======================
@@ -394,6 +407,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
     const int t_base = (MT == 2) ? half * BN : half * CH;   // its first TMEM column inside a chunk buffer
     uint32_t cc = 0;
     int staged_key = -1;
+    long long t_epi = 0, t_wait_tfull = 0, t_drain = 0;
     for (int w = blockIdx.x; w < p.total_tiles * S; w += gridDim.x) {
       const int tile = w / S, ks = w - tile * S;
       const int kbeg = (ks * p.nkb) / S, kend = ((ks + 1) * p.nkb) / S;
@@ -429,7 +443,10 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       for (int k0 = kbeg; k0 < kend; k0 += G, ++cc) {
         const uint32_t buf = cc % NBUF;
         const uint32_t bphase = (cc / NBUF) & 1;
+        const long long tC = p.dbgbuf ? clock64() : 0;
         mbar_wait(smem_u32(&tfull_bar[buf]), bphase, p.err, 4);
+        const long long tD = p.dbgbuf ? clock64() : 0;
+        t_wait_tfull += tD - tC;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * SP::kBufCols + t_base;
         if (CH >= 128) {     // 64 columns in flight per TMEM round trip (232-register budget after setmaxnreg)
@@ -466,7 +483,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+        if (p.dbgbuf) t_drain += clock64() - tD;
       }
+      const long long tE = p.dbgbuf ? clock64() : 0;
 
       // ---- split-K: park the partial tile in the workspace, wait until all S slices of this tile have
       //      arrived (they are co-resident: work items <= #SMs by construction), then every CTA reduces and
@@ -492,15 +511,15 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-        for (int ch = 0; ch < CH; ch += 16) {
-          if (((c_base + ch) >> 4) % S != ks) continue;
+        for (int ch = 0; ch < CH; ch += 32) {
+          if (((c_base + ch) >> 5) % S != ks) continue;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[ch + j] = 0.f;
+          for (int j = 0; j < 32; ++j) acc[ch + j] = 0.f;
           for (int q = 0; q < S; ++q) {
             const float4* rp = reinterpret_cast<const float4*>(p.ws) +
                                ((size_t)(tile * S + q) * (MT * BN / 4) + (t_base + ch) / 4) * kBM + row;
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
+            for (int j = 0; j < 32; j += 4) {
               const float4 v = __ldcg(rp + (size_t)(j / 4) * kBM);
               acc[ch + j] += v.x; acc[ch + j + 1] += v.y; acc[ch + j + 2] += v.z; acc[ch + j + 3] += v.w;
             }
@@ -508,7 +527,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         }
       }
       if (!(p.dbg & 2)) {
-      // ---- epilogue on the register accumulators ----
+      // ---- epilogue on the register accumulators, 32 output channels at a time ----
+      const int ty0 = (r2 / p.tiles_x) * (p.hbox * MT) + (MT == 2 ? half * p.hbox : 0);
+      const int tx0 = (r2 % p.tiles_x) * p.wbox;
       size_t opix = 0;
       if (valid) {
         if (p.out_f32) opix = ((size_t)(img * p.Hl + y) * p.Wl + x) * p.out_ld + n0 + c_base;
@@ -516,11 +537,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       }
       float h0 = 0.f, h1 = 0.f;
 #pragma unroll
-      for (int ch = 0; ch < CH; ch += 16) {
-        if (S > 1 && ((c_base + ch) >> 4) % S != ks) continue;   // another CTA of the split finishes this piece
-        float f[16];
+      for (int ch = 0; ch < CH; ch += 32) {
+        if (S > 1 && ((c_base + ch) >> 5) % S != ks) continue;   // another CTA of the split finishes this piece
+        float f[32];
 #pragma unroll
-        for (int j4 = 0; j4 < 16; j4 += 4) {      // warp-uniform float4 reads of the staged per-channel vectors
+        for (int j4 = 0; j4 < 32; j4 += 4) {      // warp-uniform float4 reads of the staged per-channel vectors
           const float4 vb = *reinterpret_cast<const float4*>(s_bias + c_base + ch + j4);
           const float4 vs = *reinterpret_cast<const float4*>(s_scale + c_base + ch + j4);
           const float4 vt = *reinterpret_cast<const float4*>(s_shift + c_base + ch + j4);
@@ -535,66 +556,74 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         }
         if (p.wout) {
 #pragma unroll
-          for (int j4 = 0; j4 < 16; j4 += 4) {
+          for (int j4 = 0; j4 < 32; j4 += 4) {
             const float4 w0 = *reinterpret_cast<const float4*>(s_head + c_base + ch + j4);
             const float4 w1 = *reinterpret_cast<const float4*>(s_head + 128 + c_base + ch + j4);
             h0 = fmaf(f[j4], w0.x, fmaf(f[j4 + 1], w0.y, fmaf(f[j4 + 2], w0.z, fmaf(f[j4 + 3], w0.w, h0))));
             h1 = fmaf(f[j4], w1.x, fmaf(f[j4 + 1], w1.y, fmaf(f[j4 + 2], w1.z, fmaf(f[j4 + 3], w1.w, h1))));
           }
-        } else if (valid && !(p.dbg & 1) && (p.out_f32 || p.omap < 0)) {
-          if (p.out_f32) {
+        } else if (p.out_f32) {
+          if (valid && !(p.dbg & 1)) {
             float4* o = reinterpret_cast<float4*>(p.out_f32 + opix + ch);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-          } else {
-            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + opix + ch);
-            uint4* ol = SPLIT ? reinterpret_cast<uint4*>(p.out_lo + opix + ch) : nullptr;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              __align__(16) __half hh[8];
-              __align__(16) __half ll[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (SPLIT) split_h(f[q * 8 + j], hh[j], ll[j]);
-                else hh[j] = __float2half_rn(fminf(fmaxf(f[q * 8 + j], -65504.f), 65504.f));
-              }
-              oh[q] = *reinterpret_cast<uint4*>(hh);
-              if (SPLIT) ol[q] = *reinterpret_cast<uint4*>(ll);
-            }
+            for (int q = 0; q < 8; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
           }
-        } else if (p.omap >= 0 && !(p.dbg & 1)) {
-          // ---- staged TMA store: this half's 128 pixel rows x 16 channels go to smem (32-byte rows,
-          //      SWIZZLE_32B so the 16-byte writes are bank-conflict free) and one elected thread hands the
-          //      slab to the TMA engine.  A 16-byte store per lane straight to global costs one L1
-          //      transaction per LANE (~38k cycles per 128x256 tile, measured); this costs ~0.5k. ----
-          __align__(16) __half hh[16];
-          __align__(16) __half ll[16];
+        } else if (!(p.dbg & 1)) {
+          // hi/lo split, packed two channels per 32-bit word
+          uint32_t hw[16], lw[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            if (SPLIT) split_h(f[j], hh[j], ll[j]);
-            else hh[j] = __float2half_rn(fminf(fmaxf(f[j], -65504.f), 65504.f));
+            const float a = fminf(fmaxf(f[2 * j], -65504.f), 65504.f), b = fminf(fmaxf(f[2 * j + 1], -65504.f), 65504.f);
+            const __half2 h2 = __floats2half2_rn(a, b);
+            hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            if (SPLIT) {
+              const float2 hf = __half22float2(h2);
+              const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
+              lw[j] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
           }
-          const uint32_t sbuf = smem_u32(s_out) + half * 8192;
-          const bool issuer = (threadIdx.x & 127) == 0;
-          if (issuer) bulk_wait_read0();                        // previous slab has left the staging buffer
-          asm volatile("bar.sync %0, 128;" ::"r"(3 + half) : "memory");
-          const uint32_t sw = (row >> 2) & 1;                   // Swizzle<1,4,3>: 16-byte chunk ^= byte-offset bit 7
-          const uint32_t r0 = sbuf + row * 32;
-          st_shared_v4(r0 + ((0 ^ sw) << 4), *reinterpret_cast<uint4*>(&hh[0]));
-          st_shared_v4(r0 + ((1 ^ sw) << 4), *reinterpret_cast<uint4*>(&hh[8]));
-          if (SPLIT) {
-            st_shared_v4(r0 + 4096 + ((0 ^ sw) << 4), *reinterpret_cast<uint4*>(&ll[0]));
-            st_shared_v4(r0 + 4096 + ((1 ^ sw) << 4), *reinterpret_cast<uint4*>(&ll[8]));
-          }
-          fence_async_smem();
-          asm volatile("bar.sync %0, 128;" ::"r"(3 + half) : "memory");
-          if (issuer) {
-            const CUtensorMap* om = p.amaps + p.omap + cls * 2;
-            const int ty0 = (r2 / p.tiles_x) * (p.hbox * MT) + (MT == 2 ? half * p.hbox : 0);
-            const int tx0 = (r2 % p.tiles_x) * p.wbox;
-            tma_store_4d(om, sbuf, n0 + c_base + ch, tx0, ty0, img);
-            if (SPLIT) tma_store_4d(om + 1, sbuf + 4096, n0 + c_base + ch, tx0, ty0, img);
-            bulk_commit();
+          if (p.store_mode == 0) {
+            // direct: every lane stores its own pixel row (one L1 transaction per lane per instruction)
+            if (valid) {
+              uint4* oh = reinterpret_cast<uint4*>(p.out_hi + opix + ch);
+              uint4* ol = SPLIT ? reinterpret_cast<uint4*>(p.out_lo + opix + ch) : nullptr;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                oh[q] = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+                if (SPLIT) ol[q] = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+              }
+            }
+          } else {
+            // warp-transposed: the warp's 32 rows x 64 bytes go through a private 2 KB smem tile (XOR-swizzled,
+            // conflict-free both ways) so that each store instruction writes 8 pixel rows x 64 contiguous
+            // bytes instead of 32 rows x 16 bytes -- 4x fewer L1 transactions, no completion wait.
+            const uint32_t wbuf = smem_u32(s_out) + (warp - 4) * 2048;
+#pragma unroll
+            for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane) {
+              const uint32_t* src = plane == 0 ? hw : lw;
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                st_shared_v4(wbuf + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4),
+                             make_uint4(src[4 * c], src[4 * c + 1], src[4 * c + 2], src[4 * c + 3]));
+              __syncwarp();
+              __half* gbase = plane == 0 ? p.out_hi : p.out_lo;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rl = i * 8 + (lane >> 2), c = lane & 3;          // row of this warp's 32, 16-byte chunk
+                uint4 v;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                             : "r"(wbuf + rl * 64 + ((c ^ ((rl >> 1) & 3)) << 4)));
+                const int rr = quarter * 32 + rl;
+                const int yy = ty0 + (rr >> p.wshift), xx = tx0 + (rr & (p.wbox - 1));
+                if (yy < p.Hl && xx < p.Wl) {
+                  const size_t o = ((size_t)(img * p.Hout + yy * p.os + (cls >> 1)) * p.Wout + xx * p.os + (cls & 1)) * p.Cout +
+                                   n0 + c_base + ch + c * 8;
+                  *reinterpret_cast<uint4*>(gbase + o) = v;
+                }
+              }
+              __syncwarp();
+            }
           }
         }
       }
@@ -615,6 +644,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         }
       }
       }
+      if (p.dbgbuf) t_epi += clock64() - tE;
       if (S > 1) {
         asm volatile("bar.sync 1, 256;" ::: "memory");          // all of this CTA's workspace reads are done
         if (et == 0) {
@@ -623,10 +653,15 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         }
       }
     }
+    t_wait_tfull_g = t_wait_tfull; t_drain_g = t_drain; t_epi_g = t_epi;
   }
 
   // ---- teardown ----
-  if (warp >= 4 && (threadIdx.x & 127) == 0) bulk_wait_all();   // staged TMA stores have left shared memory
+  if (p.dbgbuf && warp == 4 && lane == 0) {
+    p.dbgbuf[blockIdx.x * 8 + 3] = t_wait_tfull_g;
+    p.dbgbuf[blockIdx.x * 8 + 4] = t_drain_g;
+    p.dbgbuf[blockIdx.x * 8 + 5] = t_epi_g;
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -787,38 +822,6 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
       return IDC_ERR_CUDA;
     }
   }
-  // output (TMA store) maps: one [hi, lo] pair per output-parity class, 16-channel slabs, SWIZZLE_32B
-  int omap_index = -1;
-  if (op.out_buf >= 0 && !op.out_f32 && !op.fuse_out_head) {
-    omap_index = (int)amaps.size();
-    const ActBuf& ob = c->bufs[op.out_buf];
-    for (int cls = 0; cls < op.ncls; ++cls) {
-      const int cy = op.os == 2 ? (cls >> 1) : 0, cx = op.os == 2 ? (cls & 1) : 0;
-      const int Hv = (ob.H - cy + op.os - 1) / op.os, Wv = (ob.W - cx + op.os - 1) / op.os;
-      for (int part = 0; part < 2; ++part) {
-        CUtensorMap m;
-        char* base = (char*)(part == 0 ? ob.p0 : ob.p1);
-        if (!base) { amaps.push_back(amaps.back()); continue; }    // fast mode: lo unused
-        base += ((size_t)cy * ob.W + cx) * ob.C * sizeof(__half);
-        cuuint64_t dims[4] = {(cuuint64_t)ob.C, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)c->max_n};
-        cuuint64_t strides[3] = {(cuuint64_t)op.os * ob.C * 2, (cuuint64_t)op.os * ob.W * ob.C * 2,
-                                 (cuuint64_t)ob.H * ob.W * ob.C * 2};
-        cuuint32_t box[4] = {16, (cuuint32_t)op.wbox, (cuuint32_t)op.hbox, 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-          char msg[256];
-          snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled(out) failed (%d) for op %s", (int)r, op.name.c_str());
-          c->err = msg;
-          return IDC_ERR_CUDA;
-        }
-        amaps.push_back(m);
-      }
-    }
-  }
-  if (const char* e = getenv("IDC_DIRECT_STORES")) { if (atoi(e)) omap_index = -1; }
   if (cudaMalloc(&pl->d_amaps, amaps.size() * sizeof(CUtensorMap)) != cudaSuccess ||
       cudaMalloc(&pl->d_kblk, kblk.size() * sizeof(int4)) != cudaSuccess) {
     c->err = "cudaMalloc failed in umma_plan_op";
@@ -856,9 +859,11 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
     q.Hout = ob.H; q.Wout = ob.W; q.Cout = ob.C; q.os = op.os;
   }
   if (op.fuse_out_head) { q.wout = c->wout; q.bout = c->bout; }
-  q.omap = omap_index;
+  q.store_mode = 1;
+  if (const char* e = getenv("IDC_DIRECT_STORES")) { if (atoi(e)) q.store_mode = 0; }
   q.err = c->d_err;
   q.dbg = 0;
+  q.dbgbuf = nullptr;
   if (const char* e = getenv("IDC_DEBUG_SKIP")) q.dbg = atoi(e);
   // split-K for launches that cannot fill the machine even at the ctx's max batch (interactive path)
   {
@@ -867,12 +872,12 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
     if (T * 2 <= pl->num_sms && nkb >= 8 && !op.fuse_out_head && pl->mt == 1) {
       S = (int)(pl->num_sms / T);
       if (S > nkb / 4) S = nkb / 4;
-      if (S > op.bn_tile / 16) S = op.bn_tile / 16;      // one 16-column piece per CTA at least
+      if (S > op.bn_tile / 32) S = op.bn_tile / 32;      // one 32-column piece per CTA at least
       if (S < 1) S = 1;
     }
     if (const char* e = getenv("IDC_SPLIT_K")) {           // experiments; must keep all work items co-resident
       int v = atoi(e);
-      if (v >= 1 && v <= nkb && v <= op.bn_tile / 16 && pl->mt == 1 && T * v <= pl->num_sms) S = v;
+      if (v >= 1 && v <= nkb && v <= op.bn_tile / 32 && pl->mt == 1 && T * v <= pl->num_sms) S = v;
     }
     pl->split_k = S;
     pl->ws_tiles = (int)T;
@@ -900,6 +905,7 @@ cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float ou
   prm.total_tiles = op.ncls * n * prm.tiles_y * prm.tiles_x * prm.n_tiles_n;
   prm.gadd = (op.epi.gadd && c->gadd_active) ? c->gvec : nullptr;
   prm.out_ab = out_ab_fused;
+  prm.dbgbuf = c->dbgbuf;
   prm.split_k = pl->split_k;
   prm.ws = c->splitk_ws;
   prm.counters = c->splitk_counters;
