@@ -44,7 +44,7 @@ def _peaks():
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
     def __init__(self, index=0):
         threading.Thread.__init__(self, daemon=True)
@@ -53,21 +53,25 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
                 f = [s.strip() for s in line.split(",")]
                 if len(f) >= 6 and f[0].isdigit():
-                    self.samples.append(f)
+                    self.samples.append((time.perf_counter(), f))
         except Exception:
             pass
 
-    def finish(self):
+    def finish(self, t_begin=None, t_end=None):
+        """Only samples taken inside [t_begin, t_end] (the timed region) count."""
         self.stop_flag = True
         if self.proc:
             self.proc.terminate()
+        allf = [f for _, f in self.samples]
+        inside = [f for t, f in self.samples if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end)]
+        self.samples = inside if inside else allf
         sm = [int(s[0]) for s in self.samples]
         reasons = set()
         for s in self.samples:
@@ -76,7 +80,9 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         return {"sm_mhz": int(statistics.median(sm)) if sm else None,
                 "sm_max_mhz": int(self.samples[0][1]) if self.samples else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_median": (statistics.median([float(s[6]) for s in self.samples if len(s) > 6 and s[6].replace(".", "").isdigit()])
+                                   if any(len(s) > 6 for s in self.samples) else None)}
 
 
 def cpu_baseline_run(sd, budget_s, max_images, nthreads=None):
@@ -180,16 +186,18 @@ def run_ours(args):
         time.sleep(0.3)
     ctx.set_profiling(True)
     barrier()
+    t_region0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         ctx.forward_device(dL, dab, dm, 0.5, out_ab=out)
     e1.record()
     barrier()
+    t_region1 = time.perf_counter()
     ms_total = max_over_ranks(e0.elapsed_time(e1), dev)
     prof = ctx.get_profile()
     ctx.set_profiling(False)
-    clocks = sampler.finish() if sampler else None
+    clocks = sampler.finish(t_region0, t_region1) if sampler else None
     ms_step = ms_total / args.steps
     value = world * N / (ms_step * 1e-3)
 
