@@ -56,7 +56,8 @@ enum {
                                      default = 2-term split FP16 (3 MMAs / product, <=1e-3)      */
   IDC_FLAG_GLOBAL_HINTS = 1u << 3,/* global-hints branch (models/global_model/deploy_nodist.prototxt:38-172,501-527) */
   IDC_FLAG_NO_GRAPH = 1u << 4,    /* do not capture the forward into a CUDA graph               */
-  IDC_FLAG_KEEP_CONV10 = 1u << 5  /* materialise conv10_2 (debug); default fuses model_out into model10.1 */
+  IDC_FLAG_KEEP_CONV10 = 1u << 5, /* materialise conv10_2 (debug); default fuses model_out into model10.1 */
+  IDC_FLAG_CAFFE313 = 1u << 6     /* Caffe-spec 313-bin hyper-column head (deploy_nopred.prototxt:651-850) */
 };
 
 /* dtype codes for idc_load_tensor */
@@ -117,6 +118,19 @@ int idc_forward_host(idc_ctx* ctx, int n, int h, int w, const float* L_mc, const
  * host memory, or the whole [529, h/4, w/4] plane when y4 < 0. */
 int idc_set_dist_resident(idc_ctx* ctx, int on);
 int idc_fetch_dist(idc_ctx* ctx, int img, int y4, int x4, float* out_host);
+
+/* Caffe-spec 313-bin head (models/reference_model/deploy_nopred.prototxt:651-850, weight
+ * injection data/colorize_image.py:405-413).  With IDC_FLAG_CAFFE313 every forward also runs the
+ * hyper-column (conv3_pred + conv4..7_pred + conv8_pred, ReLU) and pred_313 (1x1 -> 313 logits at h/4).
+ * Extra state_dict keys: "caffe.conv{3..8}_pred.{weight,bias}" (conv3/8: [384,256,3,3]; conv4..7: Caffe
+ * Deconvolution [512,384,4,4]), "caffe.pred_313.{weight,bias}" [313,384,1,1], "caffe.pts_in_hull" [313,2].
+ *   idc_caffe313_pred_ab:    two grouped bilinear x2 deconvs (kernel [[.25,.5,.25,0],[.5,1,.5,0],[.25,.5,.25,0],0])
+ *                            -> softmax(T * logits) -> annealed mean over the 313 bin centres = pred_ab [n,2,h,w]
+ *                            (DEVICE pointer; T = 2.6 in the reference, :827-848).
+ *   idc_caffe313_dist_pixel: dist_ab_S[:, y, x] = softmax(S * upsampled logits) at ONE full-resolution
+ *                            pixel (S = 0.2, :808-820) -> 313 floats in HOST memory. */
+int idc_caffe313_pred_ab(idc_ctx* ctx, int n, float T, float* out_ab, void* stream);
+int idc_caffe313_dist_pixel(idc_ctx* ctx, int img, int y, int x, float S, float* out313_host);
 
 /* Stand-alone post-process: lab2rgb_transpose (data/colorize_image.py:20-28).
  * L [n,1,h,w] in [0,100] (NOT mean-centred), ab [n,2,h,w] -> rgb [n,h,w,3] uint8. DEVICE ptrs. */

@@ -17,6 +17,7 @@ FLAG_FAST_FP16 = 1 << 2
 FLAG_GLOBAL_HINTS = 1 << 3
 FLAG_NO_GRAPH = 1 << 4
 FLAG_KEEP_CONV10 = 1 << 5
+FLAG_CAFFE313 = 1 << 6
 F32, F64, I64 = 0, 1, 2
 
 # every symbol include/idc_b200.h declares: (name, restype, argtypes)
@@ -34,6 +35,8 @@ SYMBOLS = [
     ("idc_forward_host", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _c.c_float, _P, _P, _P, _P]),
     ("idc_set_dist_resident", _c.c_int, [_P, _c.c_int]),
     ("idc_fetch_dist", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P]),
+    ("idc_caffe313_pred_ab", _c.c_int, [_P, _c.c_int, _c.c_float, _P, _P]),
+    ("idc_caffe313_dist_pixel", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _P]),
     ("idc_lab2rgb_u8", _c.c_int, [_c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     ("idc_get_activation", _c.c_int, [_P, _c.c_char_p, _P, _c.c_size_t, _c.POINTER(_c.c_int),
                                       _c.POINTER(_c.c_int), _c.POINTER(_c.c_int)]),

@@ -72,6 +72,7 @@ void add_up(Ctx* c, const char* name, const char* dkey, const char* lo, const ch
             const char* out) {
   ConvOp op;
   op.name = name; op.kind = OP_UP; op.wkey[0] = dkey; op.wkey[1] = skey;
+  op.src_deconv[0] = true; op.src_k[0] = 4;
   const ActBuf& lb = c->bufs[c->buf_index.at(lo)];
   const ActBuf& sb = c->bufs[c->buf_index.at(skip)];
   const ActBuf& ob = c->bufs[c->buf_index.at(out)];
@@ -153,9 +154,53 @@ void build_plan(Ctx* c) {
     op.ncls = 1; op.ntaps = 1;
     op.taps[0][0] = Tap{0, 0, 0, 0, 0};
     op.Hl = ib.H; op.Wl = ib.W; op.out_buf = -1; op.os = 1;
-    op.cout = 529; op.cout_pad = 576; op.K = ib.C; op.out_f32 = true;
+    op.cout = 529; op.cout_pad = 576; op.K = ib.C; op.out_f32 = true; op.src_k[0] = 1;
     op.flops_per_image = 2.0 * op.Hl * op.Wl * 529.0 * op.K;
     c->ops.push_back(op);
+  }
+  // Caffe-spec 313-bin head (row a14): hyper-column = conv3x3(conv3_3) + sum_l deconv4x4s2(conv{4..7}_3) +
+  // conv3x3(conv8_3) -> ReLU (deploy_nopred.prototxt:651-763), then pred_313 = conv1x1 384->313 (:765-775)
+  if (c->caffe313) {
+    add_buf(c, "hyper", H / 4, W / 4, 384);
+    ConvOp op;
+    op.name = "hyper"; op.kind = OP_HYPER;
+    const char* dsrc[4] = {"conv4_3", "conv5_3", "conv6_3", "conv7_3"};
+    const char* dkey[4] = {"caffe.conv4_pred", "caffe.conv5_pred", "caffe.conv6_pred", "caffe.conv7_pred"};
+    op.nsrc = 6;
+    for (int s = 0; s < 4; ++s) {
+      op.src[s].buf = c->buf_index.at(dsrc[s]); op.src[s].s = 1; op.src[s].cin = 512;
+      op.wkey[s] = dkey[s]; op.src_deconv[s] = true; op.src_k[s] = 4;
+    }
+    op.src[4].buf = c->buf_index.at("conv3_3"); op.src[4].s = 2; op.src[4].cin = 256; op.wkey[4] = "caffe.conv3_pred";
+    op.src[5].buf = c->buf_index.at("conv8_3"); op.src[5].s = 2; op.src[5].cin = 256; op.wkey[5] = "caffe.conv8_pred";
+    op.ncls = 4; op.ntaps = 34;
+    for (int cls = 0; cls < 4; ++cls) {
+      const int py = cls >> 1, px = cls & 1;
+      const int kys[2][2] = {{1, 3}, {0, 2}};
+      const int tys[2][2] = {{0, -1}, {1, 0}};
+      int t = 0;
+      for (int s = 0; s < 4; ++s)
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b)
+            op.taps[cls][t++] = Tap{s, kys[py][a], kys[px][b], tys[py][a], tys[px][b]};
+      for (int s = 4; s < 6; ++s)
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx) op.taps[cls][t++] = Tap{s, ky, kx, py + ky - 1, px + kx - 1};
+    }
+    op.Hl = H / 8; op.Wl = W / 8; op.out_buf = c->buf_index.at("hyper"); op.os = 2;
+    op.cout = 384; op.cout_pad = 384; op.K = 4 * 4 * 512 + 2 * 9 * 256;
+    op.epi.act = ACT_RELU;
+    op.flops_per_image = 2.0 * 4 * op.Hl * op.Wl * 384.0 * op.K;
+    c->ops.push_back(op);
+
+    ConvOp pr;
+    pr.name = "pred313"; pr.kind = OP_CLASS; pr.wkey[0] = "caffe.pred_313"; pr.src_k[0] = 1;
+    pr.nsrc = 1; pr.src[0].buf = c->buf_index.at("hyper"); pr.src[0].s = 1; pr.src[0].cin = 384;
+    pr.ncls = 1; pr.ntaps = 1; pr.taps[0][0] = Tap{0, 0, 0, 0, 0};
+    pr.Hl = H / 4; pr.Wl = W / 4; pr.out_buf = -1; pr.os = 1;
+    pr.cout = 313; pr.cout_pad = 320; pr.K = 384; pr.out_f32 = true;
+    pr.flops_per_image = 2.0 * pr.Hl * pr.Wl * 313.0 * pr.K;
+    c->ops.push_back(pr);
   }
   // level 9                                                                  model.py:162-163, 86-93
   add_up(c, "up9", "model9up.0", "conv8_3", "model2short9.0", "conv2_2", "a9_1");
@@ -285,15 +330,12 @@ int pack_weights(Ctx* c, char* host) {
     float* scale = (float*)H(op.epi.scale);
     float* shift = (float*)H(op.epi.shift);
     for (int i = 0; i < op.cout_pad; ++i) { bias[i] = 0.f; scale[i] = 1.f; shift[i] = 0.f; }
-    const HostTensor* w[2] = {nullptr, nullptr};
+    const HostTensor* w[kMaxSrc] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     for (int s = 0; s < op.nsrc; ++s) {
       w[s] = find(c, op.wkey[s] + ".weight");
       const HostTensor* b = find(c, op.wkey[s] + ".bias");
-      const int cin = op.src[s].cin;
-      bool ok;
-      if (op.kind == OP_UP && s == 0) ok = check_dims(w[s], {cin, op.cout, 4, 4});
-      else if (op.kind == OP_CLASS) ok = check_dims(w[s], {op.cout, cin, 1, 1});
-      else ok = check_dims(w[s], {op.cout, cin, 3, 3});
+      const int cin = op.src[s].cin, k = op.src_k[s];
+      const bool ok = op.src_deconv[s] ? check_dims(w[s], {cin, op.cout, k, k}) : check_dims(w[s], {op.cout, cin, k, k});
       if (!ok || !check_dims(b, {op.cout})) return fail(c, IDC_ERR_KEY, "missing/bad %s.*", op.wkey[s].c_str());
       for (int i = 0; i < op.cout; ++i) bias[i] += b->data[i];
     }
@@ -311,11 +353,10 @@ int pack_weights(Ctx* c, char* host) {
     auto wval = [&](int cls, int t, int ci, int co) -> float {
       const Tap& tp = op.taps[cls][t];
       const HostTensor* ww = w[tp.src];
-      const int cin = op.src[tp.src].cin;
-      if (op.kind == OP_UP && tp.src == 0)  // ConvTranspose2d weight is [Cin][Cout][4][4]
-        return ww->data[(((size_t)ci * op.cout + co) * 4 + tp.ky) * 4 + tp.kx];
-      if (op.kind == OP_CLASS) return ww->data[(size_t)co * cin + ci];
-      return ww->data[(((size_t)co * cin + ci) * 3 + tp.ky) * 3 + tp.kx];
+      const int cin = op.src[tp.src].cin, k = op.src_k[tp.src];
+      if (op.src_deconv[tp.src])  // ConvTranspose2d / Caffe Deconvolution weight is [Cin][Cout][k][k]
+        return ww->data[(((size_t)ci * op.cout + co) * k + tp.ky) * k + tp.kx];
+      return ww->data[(((size_t)co * cin + ci) * k + tp.ky) * k + tp.kx];
     };
     if (c->simt) {
       float* dst = (float*)H(op.w_simt);
@@ -403,6 +444,12 @@ int alloc_workspace(Ctx* c) {
     }
   }
   if (c->dist) CUDA_TRY(c, cudaMalloc(&c->logits, sizeof(float) * (size_t)c->max_n * (c->H / 4) * (c->W / 4) * 576));
+  if (c->caffe313) {
+    CUDA_TRY(c, cudaMalloc(&c->logits313, sizeof(float) * (size_t)c->max_n * (c->H / 4) * (c->W / 4) * 320));
+    CUDA_TRY(c, cudaMalloc(&c->pts313, sizeof(float) * 313 * 2));
+  }
+  for (auto& op : c->ops)
+    if (op.out_f32) op.out_f32_ptr = (op.name == "pred313") ? c->logits313 : c->logits;
   if (c->glob) {
     CUDA_TRY(c, cudaMalloc(&c->gvec, sizeof(float) * (size_t)c->max_n * 512));
     CUDA_TRY(c, cudaMalloc(&c->gtmp, sizeof(float) * (size_t)2 * c->max_n * 512));
@@ -502,6 +549,7 @@ int idc_create(int device, int max_n, int h, int w, unsigned flags, idc_ctx** ou
   c->fast = (flags & IDC_FLAG_FAST_FP16) && !c->simt;
   c->dist = flags & IDC_FLAG_DIST;
   c->glob = flags & IDC_FLAG_GLOBAL_HINTS;
+  c->caffe313 = flags & IDC_FLAG_CAFFE313;
   build_plan(c);
   int rc = alloc_workspace(c);
   if (rc != IDC_OK) {
@@ -553,6 +601,11 @@ int idc_finalize_weights(idc_ctx* c) {
   std::vector<char> host(c->arena_bytes, 0);
   rc = pack_weights(c, host.data());
   if (rc != IDC_OK) return rc;
+  if (c->caffe313) {
+    const HostTensor* pts = find(c, "caffe.pts_in_hull");
+    if (!check_dims(pts, {313, 2})) return fail(c, IDC_ERR_KEY, "missing/bad caffe.pts_in_hull [313,2]");
+    CUDA_TRY(c, cudaMemcpy(c->pts313, pts->data.data(), sizeof(float) * 626, cudaMemcpyHostToDevice));
+  }
   CUDA_TRY(c, cudaMemcpy(c->arena, host.data(), c->arena_bytes, cudaMemcpyHostToDevice));
   return idc_adopt_weights(c);
 }
@@ -703,6 +756,27 @@ int idc_fetch_dist(idc_ctx* c, int img, int y4, int x4, float* out) {
   return IDC_OK;
 }
 
+int idc_caffe313_pred_ab(idc_ctx* c, int n, float T, float* out_ab, void* stream) {
+  if (!c || !out_ab || n < 1 || n > c->max_n) return IDC_ERR_ARG;
+  if (!c->caffe313) return fail(c, IDC_ERR_STATE, "ctx was not created with IDC_FLAG_CAFFE313");
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  CUDA_TRY(c, launch_decode313(c, n, T, out_ab, (cudaStream_t)stream));
+  return IDC_OK;
+}
+
+int idc_caffe313_dist_pixel(idc_ctx* c, int img, int y, int x, float S, float* out313_host) {
+  if (!c || !out313_host || img < 0 || img >= c->max_n || y < 0 || y >= c->H || x < 0 || x >= c->W) return IDC_ERR_ARG;
+  if (!c->caffe313) return fail(c, IDC_ERR_STATE, "ctx was not created with IDC_FLAG_CAFFE313");
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  float* d = nullptr;
+  CUDA_TRY(c, cudaMalloc(&d, 320 * sizeof(float)));
+  cudaError_t e = launch_dist313_pixel(c, img, y, x, S, d, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(out313_host, d, 313 * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CUDA_TRY(c, e);
+  return IDC_OK;
+}
+
 int idc_lab2rgb_u8(int device, int n, int h, int w, const float* L, const float* ab, uint8_t* rgb, void* stream) {
   if (n < 1 || h < 1 || w < 1 || !L || !ab || !rgb) return IDC_ERR_ARG;
   if (cudaSetDevice(device) != cudaSuccess) return IDC_ERR_CUDA;
@@ -829,6 +903,8 @@ int idc_destroy(idc_ctx* c) {
   for (auto& b : c->bufs) { if (b.p0) cudaFree(b.p0); if (b.p1) cudaFree(b.p1); }
   if (c->arena) cudaFree(c->arena);
   if (c->logits) cudaFree(c->logits);
+  if (c->logits313) cudaFree(c->logits313);
+  if (c->pts313) cudaFree(c->pts313);
   if (c->splitk_ws) cudaFree(c->splitk_ws);
   if (c->splitk_counters) cudaFree(c->splitk_counters);
   if (c->gvec) cudaFree(c->gvec);

@@ -275,6 +275,126 @@ cudaError_t launch_lab2rgb(int n, int h, int w, const float* L, float l_offset, 
 }
 
 // ------------------------------------------------------------------------------------------
+// Caffe-spec 313-bin decode (deploy_nopred.prototxt:776-850): the two grouped x2 "bilinear" deconvolutions
+// (kernel outer([.5,1,.5,0]), stride 2, pad 1) compose to a x4 upsample whose output 4i+r is
+//   w0[r]*a[i] + w1[r]*a[i+1],  w0 = {1,.75,.5,.25}, w1 = {0,.25,.5,.75},  a[len] = 0 (zero padding),
+// separably in y and x.  One warp per source cell (i, j) = 16 output pixels; lanes run over the 313 bins.
+// ------------------------------------------------------------------------------------------
+constexpr int kBins313 = 313;
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void load_cell313(const float* __restrict__ logits, int ld, int n, int H4, int W4, int i, int j,
+                                             int lane, float (&a)[4][10]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ii = i + (k >> 1), jj = j + (k & 1);
+    const bool ok = ii < H4 && jj < W4;
+    const float* row = logits + ((size_t)(n * H4 + (ok ? ii : 0)) * W4 + (ok ? jj : 0)) * ld;
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+      const int b = lane + 32 * q;
+      a[k][q] = (ok && b < kBins313) ? __ldg(row + b) : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) decode313_kernel(const float* __restrict__ logits, int ld, int N, int H4, int W4,
+                                                        const float* __restrict__ pts, float T, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cell = blockIdx.x * 8 + warp;
+  if (cell >= N * H4 * W4) return;
+  const int n = cell / (H4 * W4);
+  const int r = cell - n * H4 * W4;
+  const int i = r / W4, j = r - i * W4;
+  float a[4][10];
+  load_cell313(logits, ld, n, H4, W4, i, j, lane, a);
+  float pa[10], pb[10];
+#pragma unroll
+  for (int q = 0; q < 10; ++q) {
+    const int b = lane + 32 * q;
+    pa[q] = b < kBins313 ? pts[2 * b] : 0.f;
+    pb[q] = b < kBins313 ? pts[2 * b + 1] : 0.f;
+  }
+  const int H = H4 * 4, W = W4 * 4;
+  const float w0[4] = {1.f, .75f, .5f, .25f}, w1[4] = {0.f, .25f, .5f, .75f};
+#pragma unroll
+  for (int ry = 0; ry < 4; ++ry)
+#pragma unroll
+    for (int rx = 0; rx < 4; ++rx) {
+      float v[10], mx = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 10; ++q) {
+        const float top = w0[rx] * a[0][q] + w1[rx] * a[1][q];
+        const float bot = w0[rx] * a[2][q] + w1[rx] * a[3][q];
+        v[q] = (lane + 32 * q) < kBins313 ? T * (w0[ry] * top + w1[ry] * bot) : -INFINITY;
+        mx = fmaxf(mx, v[q]);
+      }
+      mx = warp_max(mx);
+      float s = 0.f, sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int q = 0; q < 10; ++q) {
+        const float e = (lane + 32 * q) < kBins313 ? expf(v[q] - mx) : 0.f;
+        s += e; sa = fmaf(e, pa[q], sa); sb = fmaf(e, pb[q], sb);
+      }
+      s = warp_sum(s); sa = warp_sum(sa); sb = warp_sum(sb);
+      if (lane == 0) {
+        const size_t o = (size_t)n * 2 * H * W + (size_t)(4 * i + ry) * W + (4 * j + rx);
+        out[o] = sa / s;
+        out[o + (size_t)H * W] = sb / s;
+      }
+    }
+}
+
+__global__ void dist313_pixel_kernel(const float* __restrict__ logits, int ld, int H4, int W4, int img, int y, int x,
+                                     float S, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int i = y >> 2, j = x >> 2, ry = y & 3, rx = x & 3;
+  float a[4][10];
+  load_cell313(logits, ld, img, H4, W4, i, j, lane, a);
+  const float w0[4] = {1.f, .75f, .5f, .25f}, w1[4] = {0.f, .25f, .5f, .75f};
+  float v[10], mx = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < 10; ++q) {
+    const float top = w0[rx] * a[0][q] + w1[rx] * a[1][q];
+    const float bot = w0[rx] * a[2][q] + w1[rx] * a[3][q];
+    v[q] = (lane + 32 * q) < kBins313 ? S * (w0[ry] * top + w1[ry] * bot) : -INFINITY;
+    mx = fmaxf(mx, v[q]);
+  }
+  mx = warp_max(mx);
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < 10; ++q) {
+    v[q] = (lane + 32 * q) < kBins313 ? expf(v[q] - mx) : 0.f;
+    s += v[q];
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int q = 0; q < 10; ++q)
+    if ((lane + 32 * q) < kBins313) out[lane + 32 * q] = v[q] / s;
+}
+
+cudaError_t launch_decode313(Ctx* c, int n, float T, float* out_ab, cudaStream_t st) {
+  const int H4 = c->H / 4, W4 = c->W / 4;
+  const int cells = n * H4 * W4;
+  decode313_kernel<<<ceil_div(cells, 8), 256, 0, st>>>(c->logits313, 320, n, H4, W4, c->pts313, T, out_ab);
+  c->launch_count++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dist313_pixel(Ctx* c, int img, int y, int x, float S, float* out313_dev, cudaStream_t st) {
+  dist313_pixel_kernel<<<1, 32, 0, st>>>(c->logits313, 320, c->H / 4, c->W / 4, img, y, x, S, out313_dev);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // global-hints MLP: 4 x (1x1 conv = dense layer, ReLU, BN).  One warp per output neuron.
 // Layer 0 consumes [hist313, ind] (glob_conv1_1) and [s_avg, ind] (glob_s_conv1_1) summed.
 // ------------------------------------------------------------------------------------------

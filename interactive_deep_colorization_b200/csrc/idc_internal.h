@@ -15,7 +15,8 @@
 
 namespace idc {
 
-constexpr int kMaxTaps = 13;  // fused up-layer: 4 deconv taps + 9 shortcut taps
+constexpr int kMaxTaps = 34;  // up-layer: 4 deconv + 9 shortcut taps; Caffe hyper-column: 4x4 deconv + 2x9 conv taps
+constexpr int kMaxSrc = 6;
 constexpr int kMaxCls = 4;    // output parity classes of a stride-2 transposed conv
 
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY02 = 2 };
@@ -66,15 +67,17 @@ struct SrcDesc {
   int cin = 0;
 };
 
-enum OpKind { OP_CONV = 0, OP_UP = 1, OP_CLASS = 2 };
+enum OpKind { OP_CONV = 0, OP_UP = 1, OP_CLASS = 2, OP_HYPER = 3 };
 
 struct ConvOp {
   std::string name;
   int kind = OP_CONV;
-  std::string wkey[2];  // state_dict keys: main conv / deconv, shortcut conv
+  std::string wkey[kMaxSrc];  // state_dict keys, one per source (main conv / deconv, shortcut conv, ...)
+  bool src_deconv[kMaxSrc] = {false, false, false, false, false, false};  // source s is a ConvTranspose2d (IOHW weights)
+  int src_k[kMaxSrc] = {3, 3, 3, 3, 3, 3};   // kernel size of source s's filter (3, 4 for the transposed convs, 1)
   std::string bnkey;
   int nsrc = 1;
-  SrcDesc src[2];
+  SrcDesc src[kMaxSrc];
   int ncls = 1;
   int ntaps = 0;                 // taps per class
   Tap taps[kMaxCls][kMaxTaps];
@@ -86,6 +89,7 @@ struct ConvOp {
   Epilogue epi;
   bool fuse_out_head = false;    // tcgen05 engine: model_out (128->2, tanh*110) in the epilogue
   bool out_f32 = false;          // store FP32 [M][cout_pad] instead of an activation (class logits)
+  float* out_f32_ptr = nullptr;  // where (ctx->logits or ctx->logits313)
   // packed weights
   float* w_simt = nullptr;       // [ncls][K][cout_pad] fp32
   __half* w_hi = nullptr;        // [ncls*cout_pad][K] fp16 (x wscale)
@@ -136,6 +140,9 @@ struct Ctx {
   float* gtmp = nullptr;   // [2][max_n][512]
   // workspace
   float* logits = nullptr;     // [max_n*(H/4)*(W/4)][cout_pad(529)]
+  float* logits313 = nullptr;  // Caffe-spec head: [max_n*(H/4)*(W/4)][320]
+  bool caffe313 = false;
+  float* pts313 = nullptr;     // [313][2] ab bin centres (device)
   float* conv10_f32 = nullptr; // SIMT: conv10_2 is a normal buffer; unused otherwise
   // split-K workspace of the tcgen05 engine (sized by umma_plan_op, allocated after planning)
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;
@@ -178,6 +185,8 @@ cudaError_t launch_out_head(Ctx* c, int n, float* out_ab, cudaStream_t st);   //
 cudaError_t launch_softmax529(Ctx* c, int n, float* out_dist, cudaStream_t st);
 cudaError_t launch_lab2rgb(int n, int h, int w, const float* L, float l_offset, const float* ab,
                            uint8_t* rgb, cudaStream_t st);
+cudaError_t launch_decode313(Ctx* c, int n, float T, float* out_ab, cudaStream_t st);
+cudaError_t launch_dist313_pixel(Ctx* c, int img, int y, int x, float S, float* out313_dev, cudaStream_t st);
 cudaError_t launch_global_mlp(Ctx* c, int n, const float* glob, cudaStream_t st);
 cudaError_t launch_act_to_nchw(Ctx* c, const ActBuf& b, int n, float* out, cudaStream_t st);
 cudaError_t launch_nchw_to_act(Ctx* c, const ActBuf& b, int n, const float* in, cudaStream_t st);

@@ -10,8 +10,8 @@
 namespace idc {
 
 struct SimtParams {
-  const float* src[2];
-  int sH[2], sW[2], sC[2], ss[2];
+  const float* src[kMaxSrc];
+  int sH[kMaxSrc], sW[kMaxSrc], sC[kMaxSrc], ss[kMaxSrc];
   int ntaps;
   int tsrc[kMaxTaps], tty[kMaxTaps], ttx[kMaxTaps], tk0[kMaxTaps];
   const float* w;  // [K][cout_pad]
@@ -135,7 +135,7 @@ cudaError_t simt_run_op(Ctx* c, ConvOp& op, int n, cudaStream_t st) {
     p.w = op.w_simt + (size_t)cls * op.K * op.cout_pad;
     p.N = n; p.Hl = op.Hl; p.Wl = op.Wl;
     if (op.out_f32) {
-      p.out = c->logits; p.Hout = op.Hl; p.Wout = op.Wl; p.os = 1; p.oy0 = 0; p.ox0 = 0;
+      p.out = op.out_f32_ptr; p.Hout = op.Hl; p.Wout = op.Wl; p.os = 1; p.oy0 = 0; p.ox0 = 0;
       p.out_ld = op.cout_pad;
     } else {
       const ActBuf& ob = c->bufs[op.out_buf];

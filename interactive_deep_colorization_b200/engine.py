@@ -19,7 +19,7 @@ class LhnContext(object):
     `SIGGRAPHGenerator(...).cuda().eval()`, /root/reference/data/colorize_image.py:221-232)."""
 
     def __init__(self, device=0, max_n=1, H=256, W=256, dist=False, engine="tcgen05", fast_fp16=False,
-                 global_hints=False, use_graph=True, keep_conv10=False):
+                 global_hints=False, use_graph=True, keep_conv10=False, caffe313=False):
         self.lib = _lib.load()
         flags = 0
         if dist:
@@ -36,6 +36,8 @@ class LhnContext(object):
             flags |= _lib.FLAG_NO_GRAPH
         if keep_conv10:
             flags |= _lib.FLAG_KEEP_CONV10
+        if caffe313:
+            flags |= _lib.FLAG_CAFFE313
         self.device, self.max_n, self.H, self.W = int(device), int(max_n), int(H), int(W)
         self.dist, self.global_hints, self.flags = bool(dist), bool(global_hints), flags
         h = ctypes.c_void_p()
@@ -134,6 +136,21 @@ class LhnContext(object):
         else:
             out = np.empty((529,), np.float32)
             _lib.check(self.h, self.lib.idc_fetch_dist(self.h, img, int(y4), int(x4), _np_ptr(out)))
+        return out
+
+    # ---- Caffe-spec 313-bin head (IDC_FLAG_CAFFE313) ----------------------------------------
+    def caffe313_pred_ab(self, n, T=2.6):
+        """Annealed-mean ab [n,2,H,W] (device tensor) from the 313-bin logits of the last forward."""
+        import torch
+        out = torch.empty((n, 2, self.H, self.W), dtype=torch.float32, device="cuda:%d" % self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.h, self.lib.idc_caffe313_pred_ab(self.h, n, float(T), out.data_ptr(), st))
+        return out
+
+    def caffe313_dist_pixel(self, img, y, x, S=0.2):
+        """dist_ab_S[:, y, x] (313 floats) at one full-resolution pixel."""
+        out = np.empty((313,), np.float32)
+        _lib.check(self.h, self.lib.idc_caffe313_dist_pixel(self.h, int(img), int(y), int(x), float(S), _np_ptr(out)))
         return out
 
     # ---- introspection (tests) -------------------------------------------------------------

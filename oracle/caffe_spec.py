@@ -42,3 +42,50 @@ def global_hints_vector(gsd, glob316):
         x = F.relu(F.linear(x, t("weight"), t("bias")))
         x = F.batch_norm(x, t("bn.running_mean"), t("bn.running_var"), t("bn.weight"), t("bn.bias"), False, 0.0, BN_EPS)
     return x
+
+
+# ---------------------------------------------------------------------------------------------
+# 313-bin hyper-column head + annealed-mean decode (row a14)
+#   models/reference_model/deploy_nopred.prototxt:651-850; kernel / centre injection
+#   data/colorize_image.py:405-413.  PARITY UNPINNED (no Caffe runtime, no vectors).
+# ---------------------------------------------------------------------------------------------
+US_KERNEL = np.array(((.25, .5, .25, 0), (.5, 1., .5, 0), (.25, .5, .25, 0), (0, 0, 0, 0)), dtype=np.float32)
+
+
+def synthetic_caffe313_state_dict(seed=777, pts_in_hull=None):
+    rng = np.random.RandomState(seed)
+    sd = {}
+    for name, cin in (("conv3_pred", 256), ("conv8_pred", 256)):
+        sd["caffe.%s.weight" % name] = (rng.standard_normal((384, cin, 3, 3)) * np.sqrt(2.0 / (6 * cin * 9))).astype(np.float32)
+        sd["caffe.%s.bias" % name] = rng.uniform(-0.05, 0.05, 384).astype(np.float32)
+    for l in (4, 5, 6, 7):     # Caffe Deconvolution blobs are [Cin, Cout, kh, kw]
+        sd["caffe.conv%d_pred.weight" % l] = (rng.standard_normal((512, 384, 4, 4)) * np.sqrt(2.0 / (6 * 512 * 4))).astype(np.float32)
+        sd["caffe.conv%d_pred.bias" % l] = rng.uniform(-0.05, 0.05, 384).astype(np.float32)
+    sd["caffe.pred_313.weight"] = (rng.standard_normal((313, 384, 1, 1)) * (3.0 / np.sqrt(384))).astype(np.float32)
+    sd["caffe.pred_313.bias"] = rng.uniform(-0.1, 0.1, 313).astype(np.float32)
+    if pts_in_hull is not None:
+        sd["caffe.pts_in_hull"] = np.asarray(pts_in_hull, dtype=np.float32)
+    return sd
+
+
+def caffe313_head(csd, inter, T=2.6, S=0.2, return_logits=False):
+    """inter: intermediates of oracle/lhn_ref.lhn_forward (conv3_3 ... conv8_3 are the *norm blobs).
+    -> (pred_ab [N,2,H,W], dist_ab_S [N,313,H,W])"""
+    t = lambda k: torch.as_tensor(np.asarray(csd[k]), dtype=torch.float32)
+    h = F.conv2d(inter["conv3_3"], t("caffe.conv3_pred.weight"), t("caffe.conv3_pred.bias"), padding=1)
+    for l in (4, 5, 6, 7):
+        h = h + F.conv_transpose2d(inter["conv%d_3" % l], t("caffe.conv%d_pred.weight" % l), t("caffe.conv%d_pred.bias" % l),
+                                   stride=2, padding=1)
+    h = h + F.conv2d(inter["conv8_3"], t("caffe.conv8_pred.weight"), t("caffe.conv8_pred.bias"), padding=1)
+    h = F.relu(h)                                                          # relu345678_pred
+    logits = F.conv2d(h, t("caffe.pred_313.weight"), t("caffe.pred_313.bias"))
+    k = torch.from_numpy(US_KERNEL)[None, None].repeat(313, 1, 1, 1)       # data/colorize_image.py:409-413
+    up = F.conv_transpose2d(logits, k, None, stride=2, padding=1, groups=313)        # pred_313_us
+    up = F.conv_transpose2d(up, k, None, stride=2, padding=1, groups=313)            # pred_313_rs
+    dist_S = F.softmax(up * S, dim=1)                                      # scale_S + dist_ab_S
+    dist_T = F.softmax(up * T, dim=1)                                      # scale_T + dist_ab (T)
+    pts = t("caffe.pts_in_hull")                                           # pred_ab weights = pts_in_hull.T (:405-407)
+    pred_ab = torch.einsum("nbhw,bc->nchw", dist_T, pts)
+    if return_logits:
+        return pred_ab, dist_S, logits, h
+    return pred_ab, dist_S

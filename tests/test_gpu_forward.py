@@ -179,3 +179,53 @@ def test_global_hints_branch(synth_sd):
         torch.cuda.synchronize()
         assert util.maxabs(r0["ab"], ref_noglob) <= TOL_AB, engine
         ctx.close()
+
+
+def test_caffe313_head(synth_sd):
+    """row a14 (Caffe spec, parity unpinned): hyper-column + pred_313 + bilinear x4 + annealed mean, against
+    oracle/caffe_spec.caffe313_head (which uses the literal grouped Deconvolution kernels)."""
+    from oracle import caffe_spec
+    pts = np.load(util.os.path.join(util.GOLDEN, "pts_in_hull.npy"))
+    csd = caffe_spec.synthetic_caffe313_state_dict(pts_in_hull=pts)
+    sd = dict(synth_sd)
+    sd.update({k: torch.from_numpy(v) for k, v in csd.items()})
+    L, ab, m = util.small_batch(2, 64, seed=500)
+    _, inter = util.oracle_forward(synth_sd, L, ab, m, 0.5, intermediates=True)
+    with torch.no_grad():
+        pred_ref, distS_ref, logits_ref, hyper_ref = caffe_spec.caffe313_head(csd, inter, return_logits=True)
+    assert float(pred_ref.abs().max()) > 5.0
+    for engine in ("simt", "tcgen05"):
+        ctx = util.make_ctx(sd, 64, 64, max_n=2, engine=engine, caffe313=True)
+        ctx.forward_device(util.dev(L), util.dev(ab), util.dev(m), 0.5)
+        torch.cuda.synchronize()
+        assert util.maxabs(ctx.get_activation("hyper", 2), hyper_ref) < 3e-4, engine
+        pred = ctx.caffe313_pred_ab(2)
+        torch.cuda.synchronize()
+        err = util.maxabs(pred, pred_ref)
+        print("caffe313 %s: max|d pred_ab| = %.3e" % (engine, err))
+        assert err <= TOL_AB, (engine, err)
+        for (y, x) in ((0, 0), (13, 62), (63, 63), (31, 7)):
+            d = ctx.caffe313_dist_pixel(1, y, x)
+            assert util.maxabs(d, distS_ref[1, :, y, x]) < 1e-5, (engine, y, x)
+            assert abs(float(d.sum()) - 1.0) < 1e-5
+        ctx.close()
+
+
+def test_config4_512_global_hints(synth_sd):
+    """BASELINE config 4: 512x512 with a global-hints histogram vector (2 of the 16 images, oracle-checked)."""
+    from oracle import caffe_spec
+    gsd = caffe_spec.synthetic_glob_state_dict()
+    sd = dict(synth_sd)
+    sd.update({k: torch.from_numpy(v) for k, v in gsd.items()})
+    L, ab, m = synth.synthetic_batch(2, 512, seed=40, max_hints=10)
+    glob_ab, sat = synth.synthetic_glob(2, seed=3)
+    glob = np.ascontiguousarray(np.concatenate([glob_ab, sat], axis=1).astype(np.float32))
+    gvec = caffe_spec.global_hints_vector(gsd, glob)
+    ref = util.oracle_forward(synth_sd, L, ab, m, 0.5, glob_add=gvec)
+    ctx = util.make_ctx(sd, 512, 512, max_n=2, global_hints=True)
+    r = ctx.forward_host(L, ab, m, 0.5, glob=glob, want_rgb=True)
+    err = util.maxabs(r["ab"], ref)
+    print("512x512 + global hints: max|d ab| = %.3e" % err)
+    assert err <= TOL_AB
+    assert r["rgb"].shape == (2, 512, 512, 3)
+    ctx.close()
