@@ -137,6 +137,15 @@ int idc_caffe313_dist_pixel(idc_ctx* ctx, int img, int y, int x, float S, float*
 int idc_lab2rgb_u8(int device, int n, int h, int w, const float* L, const float* ab,
                    uint8_t* rgb, void* stream);
 
+/* f1 (steps either side of the network), float64 like the reference's numpy/skimage/scipy path; DEVICE ptrs.
+ * idc_rgb2lab_f64:      skimage color.rgb2lab of uint8 RGB [n,h,w,3] -> Lab planes [n,3,h,w] float64
+ *                       (data/colorize_image.py:31-36, :172-178 image prep, :196-198 _set_out_ab_).
+ * idc_zoom_lab2rgb_u8:  get_img_fullres (:123-131): scipy.ndimage.zoom(order=1) of ab [2,h_in,w_in] to
+ *                       [h,w], then lab2rgb_transpose with the full-resolution L [h,w] -> uint8 [h,w,3]. */
+int idc_rgb2lab_f64(int device, int n, int h, int w, const uint8_t* rgb, double* lab, void* stream);
+int idc_zoom_lab2rgb_u8(int device, int h_in, int w_in, const double* ab, int h, int w, const double* L_full,
+                        uint8_t* rgb, void* stream);
+
 /* ---- introspection / test hooks (used by tests/, never by the product path) ---- */
 /* Copy a named activation ("conv1_2", "a8_1", ... see DESIGN.md) of the LAST forward to
  * out [n,C,H,W] FP32 device memory; *c,*h,*w receive its shape. */

@@ -161,8 +161,9 @@ class ColorizeImageBase(object):
 class ColorizeImageB200(ColorizeImageBase):
     """<-> ColorizeImageTorch (reference :201-276)."""
 
-    def __init__(self, Xd=256, maskcent=False, engine="tcgen05", fast_fp16=False):
+    def __init__(self, Xd=256, maskcent=False, engine="tcgen05", fast_fp16=False, gpu_prepost=True):
         print('ColorizeImageB200 instantiated')
+        self.gpu_prepost = gpu_prepost    # quantised output_ab and the full-res render on the GPU (row f1)
         ColorizeImageBase.__init__(self, Xd)
         self.l_norm = 1.
         self.ab_norm = 1.
@@ -210,6 +211,20 @@ class ColorizeImageB200(ColorizeImageBase):
 
     def get_img_gray(self):
         return lab2rgb_transpose(self.img_l, np.zeros((2, self.Xd, self.Xd)))
+
+    # ----- row f1: the numpy/scipy steps either side of the network, on the GPU when a net is set -----
+    def _set_out_ab_(self):
+        if not (self.gpu_prepost and self.net_set):
+            return ColorizeImageBase._set_out_ab_(self)
+        from . import prepost
+        self.output_lab = prepost.rgb2lab_gpu(self.output_rgb, self.net.b200_device)
+        self.output_ab = self.output_lab[1:]
+
+    def get_img_fullres(self):
+        if not (self.gpu_prepost and self.net_set):
+            return ColorizeImageBase.get_img_fullres(self)
+        from . import prepost
+        return prepost.fullres_rgb_gpu(self.output_ab, self.img_l_fullres, self.net.b200_device)
 
 
 class _LazyUpsampledDist(object):

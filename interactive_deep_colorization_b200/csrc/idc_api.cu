@@ -783,6 +783,19 @@ int idc_lab2rgb_u8(int device, int n, int h, int w, const float* L, const float*
   return launch_lab2rgb(n, h, w, L, 0.0f, ab, rgb, (cudaStream_t)stream) == cudaSuccess ? IDC_OK : IDC_ERR_CUDA;
 }
 
+int idc_rgb2lab_f64(int device, int n, int h, int w, const uint8_t* rgb, double* lab, void* stream) {
+  if (n < 1 || h < 1 || w < 1 || !rgb || !lab) return IDC_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return IDC_ERR_CUDA;
+  return launch_rgb2lab(n, h, w, rgb, lab, (cudaStream_t)stream) == cudaSuccess ? IDC_OK : IDC_ERR_CUDA;
+}
+
+int idc_zoom_lab2rgb_u8(int device, int h_in, int w_in, const double* ab, int h, int w, const double* L_full,
+                        uint8_t* rgb, void* stream) {
+  if (h_in < 1 || w_in < 1 || h < 1 || w < 1 || !ab || !L_full || !rgb) return IDC_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return IDC_ERR_CUDA;
+  return launch_zoom_lab2rgb(ab, h_in, w_in, L_full, h, w, rgb, (cudaStream_t)stream) == cudaSuccess ? IDC_OK : IDC_ERR_CUDA;
+}
+
 int idc_get_activation(idc_ctx* c, const char* name, float* out, size_t out_floats, int* ch, int* h, int* w) {
   if (!c || !name) return IDC_ERR_ARG;
   auto it = c->buf_index.find(name);

@@ -267,6 +267,86 @@ __global__ void lab2rgb_kernel(const float* __restrict__ L, float l_offset, cons
   rgb[i * 3 + 2] = (uint8_t)B;
 }
 
+// ------------------------------------------------------------------------------------------
+// f1: the steps either side of the network on the GPU, float64 like numpy/skimage/scipy.
+//   rgb2lab_kernel       uint8 RGB -> Lab planes (skimage rgb2lab; data/colorize_image.py:31-36,172-178,196-198)
+//   zoom_lab2rgb_kernel  scipy.ndimage.zoom(order=1) of the ab planes to the full-resolution grid +
+//                        lab2rgb_transpose with the full-resolution L (get_img_fullres, :123-131)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double srgb_inv_gamma(double c) {
+  return c > 0.04045 ? pow((c + 0.055) / 1.055, 2.4) : c / 12.92;
+}
+__device__ __forceinline__ double lab_f(double t) { return t > 0.008856 ? cbrt(t) : 7.787 * t + 16.0 / 116.0; }
+
+__global__ void rgb2lab_kernel(const uint8_t* __restrict__ rgb, int N, int HW, double* __restrict__ lab) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * HW) return;
+  const int n = (int)(i / HW);
+  const size_t r = i - (size_t)n * HW;
+  const double R = srgb_inv_gamma(rgb[i * 3 + 0] / 255.0), G = srgb_inv_gamma(rgb[i * 3 + 1] / 255.0),
+               B = srgb_inv_gamma(rgb[i * 3 + 2] / 255.0);
+  const double X = (0.412453 * R + 0.357580 * G + 0.180423 * B) / 0.95047;
+  const double Y = (0.212671 * R + 0.715160 * G + 0.072169 * B) / 1.0;
+  const double Z = (0.019334 * R + 0.119193 * G + 0.950227 * B) / 1.08883;
+  const double fx = lab_f(X), fy = lab_f(Y), fz = lab_f(Z);
+  double* o = lab + (size_t)n * 3 * HW + r;
+  o[0] = 116.0 * fy - 16.0;
+  o[HW] = 500.0 * (fx - fy);
+  o[2 * (size_t)HW] = 200.0 * (fy - fz);
+}
+
+__device__ __forceinline__ void lab_to_rgb_u8(double l, double a, double b, uint8_t* out) {
+  const double fy = (l + 16.0) / 116.0;
+  const double fx = a / 500.0 + fy;
+  double fz = fy - b / 200.0;
+  if (fz < 0.0) fz = 0.0;
+  const double X = lab_finv(fx) * 0.95047, Y = lab_finv(fy) * 1.0, Z = lab_finv(fz) * 1.08883;
+  double R = 3.240481343200526 * X + -1.5371515162713185 * Y + -0.4985363261688878 * Z;
+  double G = -0.9692549499965682 * X + 1.8759900014898907 * Y + 0.04155592655829284 * Z;
+  double B = 0.05564663913517716 * X + -0.20404133836651123 * Y + 1.0573110696453443 * Z;
+  R = srgb_gamma(R); G = srgb_gamma(G); B = srgb_gamma(B);
+  out[0] = (uint8_t)(fmin(fmax(R, 0.0), 1.0) * 255.0);
+  out[1] = (uint8_t)(fmin(fmax(G, 0.0), 1.0) * 255.0);
+  out[2] = (uint8_t)(fmin(fmax(B, 0.0), 1.0) * 255.0);
+}
+
+// scipy.ndimage.zoom(order=1, grid_mode=False): output o samples input coordinate o * (in - 1) / (out - 1)
+__global__ void zoom_lab2rgb_kernel(const double* __restrict__ ab, int hin, int win, const double* __restrict__ Lfull,
+                                    int H, int W, uint8_t* __restrict__ rgb) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)H * W) return;
+  const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+  const double cy = H > 1 ? (double)y * (double)(hin - 1) / (double)(H - 1) : 0.0;
+  const double cx = W > 1 ? (double)x * (double)(win - 1) / (double)(W - 1) : 0.0;
+  int y0 = (int)floor(cy), x0 = (int)floor(cx);
+  if (y0 > hin - 2) y0 = hin - 2 < 0 ? 0 : hin - 2;
+  if (x0 > win - 2) x0 = win - 2 < 0 ? 0 : win - 2;
+  const double ty = cy - y0, tx = cx - x0;
+  const int y1 = y0 + 1 < hin ? y0 + 1 : y0, x1 = x0 + 1 < win ? x0 + 1 : x0;
+  double v[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const double* p = ab + (size_t)c * hin * win;
+    const double top = (1.0 - tx) * p[(size_t)y0 * win + x0] + tx * p[(size_t)y0 * win + x1];
+    const double bot = (1.0 - tx) * p[(size_t)y1 * win + x0] + tx * p[(size_t)y1 * win + x1];
+    v[c] = (1.0 - ty) * top + ty * bot;
+  }
+  lab_to_rgb_u8(Lfull[i], v[0], v[1], rgb + i * 3);
+}
+
+cudaError_t launch_rgb2lab(int n, int h, int w, const uint8_t* rgb, double* lab, cudaStream_t st) {
+  const size_t tot = (size_t)n * h * w;
+  rgb2lab_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(rgb, n, h * w, lab);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_zoom_lab2rgb(const double* ab, int hin, int win, const double* Lfull, int H, int W, uint8_t* rgb,
+                                cudaStream_t st) {
+  const size_t tot = (size_t)H * W;
+  zoom_lab2rgb_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(ab, hin, win, Lfull, H, W, rgb);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_lab2rgb(int n, int h, int w, const float* L, float l_offset, const float* ab, uint8_t* rgb,
                            cudaStream_t st) {
   const size_t tot = (size_t)n * h * w;

@@ -1,0 +1,51 @@
+"""GPU versions of the steps either side of the network.
+
+    rgb2lab_gpu        skimage color.rgb2lab on uint8 RGB  (reference data/colorize_image.py:31-36,172-178,196-198)
+    fullres_rgb_gpu    get_img_fullres (:123-131): scipy zoom(order=1) of ab + Lab->RGB at full resolution
+
+float64 arithmetic on the device, like the reference's numpy path.  torch supplies device memory only.
+"""
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def rgb2lab_gpu(rgb_u8, device=0):
+    """HxWx3 (or NxHxWx3) uint8 -> 3xHxW (or Nx3xHxW) float64 numpy, == color.rgb2lab(...).transpose."""
+    torch = _torch()
+    a = np.ascontiguousarray(rgb_u8)
+    assert a.dtype == np.uint8 and a.shape[-1] == 3
+    single = a.ndim == 3
+    if single:
+        a = a[None]
+    n, h, w = a.shape[:3]
+    d_rgb = torch.from_numpy(a).to("cuda:%d" % device)
+    d_lab = torch.empty((n, 3, h, w), dtype=torch.float64, device=d_rgb.device)
+    st = torch.cuda.current_stream(d_rgb.device).cuda_stream
+    rc = _lib.load().idc_rgb2lab_f64(device, n, h, w, d_rgb.data_ptr(), d_lab.data_ptr(), st)
+    if rc != _lib.IDC_OK:
+        raise _lib.IdcError(rc, "idc_rgb2lab_f64 failed")
+    out = d_lab.cpu().numpy()
+    return out[0] if single else out
+
+
+def fullres_rgb_gpu(ab, l_fullres, device=0):
+    """ab [2,h,w] (any float), l_fullres [1,H,W] or [H,W] float64 -> uint8 [H,W,3]."""
+    torch = _torch()
+    ab = np.ascontiguousarray(ab, dtype=np.float64)
+    L = np.ascontiguousarray(np.asarray(l_fullres, dtype=np.float64).reshape(l_fullres.shape[-2], l_fullres.shape[-1]))
+    H, W = L.shape
+    d_ab = torch.from_numpy(ab).to("cuda:%d" % device)
+    d_L = torch.from_numpy(L).to(d_ab.device)
+    d_rgb = torch.empty((H, W, 3), dtype=torch.uint8, device=d_ab.device)
+    st = torch.cuda.current_stream(d_ab.device).cuda_stream
+    rc = _lib.load().idc_zoom_lab2rgb_u8(device, ab.shape[1], ab.shape[2], d_ab.data_ptr(), H, W, d_L.data_ptr(),
+                                         d_rgb.data_ptr(), st)
+    if rc != _lib.IDC_OK:
+        raise _lib.IdcError(rc, "idc_zoom_lab2rgb_u8 failed")
+    return d_rgb.cpu().numpy()

@@ -113,7 +113,10 @@ def test_wrapper_api_end_to_end(synth_sd):
     d = np.abs(rgb.astype(int) - g["mc0_kat_rgb"].astype(int))
     assert d.max() <= 1 and (d > 0).mean() < 2e-3
     assert np.max(np.abs(cm.output_ab - g["mc0_kat_output_ab"])) < 1.5     # 1 uint8 step in ab units
-    assert cm.get_img_fullres().shape == (256, 256, 3)
+    full = cm.get_img_fullres()                      # GPU zoom + Lab->RGB (row f1)
+    assert full.shape == (256, 256, 3)
+    d = np.abs(full.astype(int) - color_ref.lab2rgb_transpose(cm.img_l_fullres, cm.output_ab).astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
     cd = CI.ColorizeImageB200Dist(Xd=256, maskcent=True)
     cd.prep_net(state_dict=synth_sd)
     cd.set_image(g["img_rgb"])
@@ -231,3 +234,20 @@ def test_config4_512_global_hints(synth_sd):
     assert err <= TOL_AB
     assert r["rgb"].shape == (2, 512, 512, 3)
     ctx.close()
+
+
+def test_prepost_gpu_kernels_match_numpy_scipy():
+    """row f1: float64 GPU rgb2lab and zoom(order=1)+lab2rgb against the numpy/scipy restatements."""
+    from scipy.ndimage import zoom
+    from interactive_deep_colorization_b200 import prepost
+    rs = np.random.RandomState(5)
+    rgb = rs.randint(0, 256, (2, 37, 53, 3)).astype(np.uint8)
+    lab = prepost.rgb2lab_gpu(rgb)
+    for i in range(2):
+        assert np.max(np.abs(lab[i] - color_ref.rgb2lab_transpose(rgb[i]))) < 1e-10
+    ab = rs.uniform(-80, 80, (2, 32, 32))
+    Lf = rs.uniform(0, 100, (1, 75, 91))
+    got = prepost.fullres_rgb_gpu(ab, Lf)
+    ref = color_ref.lab2rgb_transpose(Lf, zoom(ab, (1, 75 / 32., 91 / 32.), order=1))
+    d = np.abs(got.astype(int) - ref.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3, (d.max(), (d > 0).mean())
