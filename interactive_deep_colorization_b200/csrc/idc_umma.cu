@@ -25,6 +25,10 @@
 
 #include "idc_internal.h"
 
+#ifndef IDC_CTA_COUNTERS
+#define IDC_CTA_COUNTERS 0   // 1: per-CTA cycle counters for tools/cta_counters.py (costs a few % in the hot loops)
+#endif
+
 namespace idc {
 
 constexpr int kBM = 128;      // pixels per tile (UMMA M)
@@ -345,16 +349,16 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         for (int k0 = kbeg; k0 < kend; k0 += G, ++cc) {
           const uint32_t buf = cc % NBUF;
           const uint32_t bphase = (cc / NBUF) & 1;
-          const long long tA = p.dbgbuf ? clock64() : 0;
+          const long long tA = (IDC_CTA_COUNTERS && p.dbgbuf) ? clock64() : 0;
           mbar_wait(smem_u32(&tempty_bar[buf]), bphase ^ 1, p.err, 2);
-          if (p.dbgbuf) t_wait_tempty += clock64() - tA;
+          if (IDC_CTA_COUNTERS && p.dbgbuf) t_wait_tempty += clock64() - tA;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * SP::kBufCols;
           const int k1 = (k0 + G < kend) ? k0 + G : kend;
           for (int k = k0; k < k1; ++k) {
-            const long long tB = p.dbgbuf ? clock64() : 0;
+            const long long tB = (IDC_CTA_COUNTERS && p.dbgbuf) ? clock64() : 0;
             mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 3);
-            if (p.dbgbuf) t_wait_full += clock64() - tB;
+            if (IDC_CTA_COUNTERS && p.dbgbuf) t_wait_full += clock64() - tB;
             tc_fence_after();
             if (elect_one()) {
             const uint32_t sa = smem_u32(smem + stage * SP::kStageBytes);
@@ -394,7 +398,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           }
         }
       }
-      if (p.dbgbuf && lane == 0) {
+      if (IDC_CTA_COUNTERS && p.dbgbuf && lane == 0) {
         p.dbgbuf[blockIdx.x * 8 + 0] = clock64() - t_start;
         p.dbgbuf[blockIdx.x * 8 + 1] = t_wait_tempty;
         p.dbgbuf[blockIdx.x * 8 + 2] = t_wait_full;
@@ -448,9 +452,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       for (int k0 = kbeg; k0 < kend; k0 += G, ++cc) {
         const uint32_t buf = cc % NBUF;
         const uint32_t bphase = (cc / NBUF) & 1;
-        const long long tC = p.dbgbuf ? clock64() : 0;
+        const long long tC = (IDC_CTA_COUNTERS && p.dbgbuf) ? clock64() : 0;
         mbar_wait(smem_u32(&tfull_bar[buf]), bphase, p.err, 4);
-        const long long tD = p.dbgbuf ? clock64() : 0;
+        const long long tD = (IDC_CTA_COUNTERS && p.dbgbuf) ? clock64() : 0;
         t_wait_tfull += tD - tC;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * SP::kBufCols + t_base;
@@ -488,9 +492,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
-        if (p.dbgbuf) t_drain += clock64() - tD;
+        if (IDC_CTA_COUNTERS && p.dbgbuf) t_drain += clock64() - tD;
       }
-      const long long tE = p.dbgbuf ? clock64() : 0;
+      const long long tE = (IDC_CTA_COUNTERS && p.dbgbuf) ? clock64() : 0;
 
       // ---- split-K: park the partial tile in the workspace, wait until all S slices of this tile have
       //      arrived (they are co-resident: work items <= #SMs by construction), then every CTA reduces and
@@ -651,7 +655,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         }
       }
       }
-      if (p.dbgbuf) t_epi += clock64() - tE;
+      if (IDC_CTA_COUNTERS && p.dbgbuf) t_epi += clock64() - tE;
       if (S > 1) {
         asm volatile("bar.sync 1, 256;" ::: "memory");          // all of this CTA's workspace reads are done
         if (et == 0) {
@@ -664,7 +668,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
   }
 
   // ---- teardown ----
-  if (p.dbgbuf && warp == 4 && lane == 0) {
+  if (IDC_CTA_COUNTERS && p.dbgbuf && warp == 4 && lane == 0) {
     p.dbgbuf[blockIdx.x * 8 + 3] = t_wait_tfull_g;
     p.dbgbuf[blockIdx.x * 8 + 4] = t_drain_g;
     p.dbgbuf[blockIdx.x * 8 + 5] = t_epi_g;
