@@ -165,6 +165,55 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA pairs (cta_group::2): the leader (cluster rank 0) issues M=256 MMAs over both SMs; each CTA loads its
+//      own 128 pixel rows of A and HALF of the weight tile, so every SM reads 8 KB of operands per MMA
+//      instead of 12 KB and the weight tile crosses L2->SM once per pair.  Protocol after DeepGEMM/CUTLASS:
+//      TMA (cta_group::2) signals the leader's `full` barrier, tcgen05.commit multicasts to both CTAs'
+//      `empty` / `tfull` barriers, the accumulate warps of both CTAs arrive on the leader's `tempty`. ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_rank0(uint32_t local_bar) {   // arrive on the SAME barrier of cluster rank 0
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(local_bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {          // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -200,8 +249,8 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 // kind::f16 instruction descriptor: A=B=F16, D=F32, both K-major, M=128, N=BN.
-__host__ __device__ constexpr uint32_t make_idesc(int bn) {
-  return (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int bn, int m = kBM) {
+  return (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // two floats -> packed f16x2 (low half = a), saturating to +-65504 instead of inf (one F2FP instruction)
@@ -217,10 +266,10 @@ __device__ __forceinline__ void split_h(float v, __half& hi, __half& lo) {
   lo = __float2half_rn(v - __half2float(hi));
 }
 
-template <int BN, int MT, bool SPLIT>
+template <int BN, int MT, int CG, bool SPLIT>
 struct SmemPlan {
   static constexpr int kABytes = MT * kBM * kBK * 2;            // MT M-tiles of 128 pixels x 64 ch FP16 (16 KB each)
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = (BN / CG) * kBK * 2;          // CG == 2: each CTA of the pair holds half of the weight tile
   static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kBBytes);
   static constexpr int kTail = 3 * BN * 4 + 272 * 4 + 256 + 128 * 2 * 4;  // epi vecs, head, barriers, head reduce
   static constexpr int kOutStage = 16384;                         // epilogue staging for TMA stores: 2 halves x (hi 4 KB + lo 4 KB)
@@ -232,17 +281,19 @@ struct SmemPlan {
   static constexpr int kTmemCols = (kNBuf * kBufCols <= 128) ? 128 : (kNBuf * kBufCols <= 256 ? 256 : 512);
   static constexpr int kCH = (MT == 2) ? BN : BN / 2;            // accumulator columns per accumulate thread
   static_assert(kStages >= 2, "need at least a double-buffered operand ring");
+  static_assert(CG == 1 || (MT == 1 && BN == 256), "pairs are implemented for the 128x256 tile");
 };
 
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <int BN, int MT, bool SPLIT>
+template <int BN, int MT, int CG, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_constant__ CUtensorMap bmap_lo,
                  const UmmaParams p) {
-  using SP = SmemPlan<BN, MT, SPLIT>;
+  using SP = SmemPlan<BN, MT, CG, SPLIT>;
   constexpr int STAGES = SP::kStages;
+  constexpr bool PAIR = CG == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_out = smem + STAGES * SP::kStageBytes;              // 1024-aligned (stage sizes are multiples of 1 KB)
@@ -267,25 +318,35 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
     for (int i = threadIdx.x; i < 256; i += kThreads) s_head[i] = p.wout[i];
     if (threadIdx.x < 2) s_head[256 + threadIdx.x] = p.bout[threadIdx.x];
   }
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&full_bar[s]), CG);        // pairs: both producers arrive on the leader's barrier
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int a = 0; a < NBUF; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), 8);      // one arrive per accumulate warp
+      mbar_init(smem_u32(&tempty_bar[a]), 8 * CG);  // one arrive per accumulate warp (of both CTAs on the leader)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (PAIR) cluster_sync_all();                      // peer barriers exist before anything can arrive on them
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
-                 "r"((uint32_t)SP::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                   "r"((uint32_t)SP::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                   "r"((uint32_t)SP::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
@@ -300,50 +361,61 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < p.total_tiles * S; w += gridDim.x) {
+      for (int w = blockIdx.x / CG; w < p.total_tiles * S; w += gridDim.x / CG) {
         const int tile = w / S, ks = w - tile * S;
         const int kbeg = (ks * p.nkb) / S, kend = ((ks + 1) * p.nkb) / S;
         // tile order: n-tile fastest, then output-parity class, then spatial tile, then image -- CTAs that
-        // run together share the A tile (all n-tiles) and the source rows (all 4 classes of an up-layer)
+        // run together share the A tile (all n-tiles) and the source rows (all 4 classes of an up-layer).
+        // Pairs: `tile` counts M-tile PAIRS; this CTA takes M-tile 2*pair + rank.
         int r = tile;
         const int nt = r % p.n_tiles_n;
         r /= p.n_tiles_n;
         const int cls = r % p.ncls;
         r /= p.ncls;
+        if (PAIR) r = 2 * r + (int)cta_rank;
         const int img = r / tiles_per_img;
         r -= img * tiles_per_img;
         const int y0 = (r / p.tiles_x) * (p.hbox * MT), x0 = (r % p.tiles_x) * p.wbox;
-        const int brow = cls * p.cout_pad + nt * BN;
+        const int brow = cls * p.cout_pad + nt * BN + (int)cta_rank * (BN / CG);
         const int4* kb = p.kblk + cls * p.nkb;                  // read-only table in global memory (L1-resident)
         for (int k = kbeg; k < kend; ++k) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 1);
           if (elect_one()) {
             const uint32_t fb = smem_u32(&full_bar[stage]);
-            mbar_expect_tx(fb, SP::kStageBytes);
             const int4 e = __ldg(kb + k);
             const uint32_t sa = smem_u32(smem + stage * SP::kStageBytes);
             const CUtensorMap* am = p.amaps + e.x;
-            tma_load_4d(sa, am, fb, e.y, x0 + e.w, y0 + e.z, img);
-            if (SPLIT) tma_load_4d(sa + SP::kABytes, am + 1, fb, e.y, x0 + e.w, y0 + e.z, img);
             const uint32_t sb = sa + (SPLIT ? 2 : 1) * SP::kABytes;
-            tma_load_2d(sb, &bmap_hi, fb, k * kBK, brow);
-            if (SPLIT) tma_load_2d(sb + SP::kBBytes, &bmap_lo, fb, k * kBK, brow);
+            if (PAIR) {
+              // every byte of both CTAs lands on the LEADER's barrier
+              if (leader) mbar_expect_tx(fb, 2 * SP::kStageBytes); else mbar_arrive_rank0(fb);
+              tma_load_4d_pair(sa, am, fb, e.y, x0 + e.w, y0 + e.z, img);
+              if (SPLIT) tma_load_4d_pair(sa + SP::kABytes, am + 1, fb, e.y, x0 + e.w, y0 + e.z, img);
+              tma_load_2d_pair(sb, &bmap_hi, fb, k * kBK, brow);
+              if (SPLIT) tma_load_2d_pair(sb + SP::kBBytes, &bmap_lo, fb, k * kBK, brow);
+            } else {
+              mbar_expect_tx(fb, SP::kStageBytes);
+              tma_load_4d(sa, am, fb, e.y, x0 + e.w, y0 + e.z, img);
+              if (SPLIT) tma_load_4d(sa + SP::kABytes, am + 1, fb, e.y, x0 + e.w, y0 + e.z, img);
+              tma_load_2d(sb, &bmap_hi, fb, k * kBK, brow);
+              if (SPLIT) tma_load_2d(sb + SP::kBBytes, &bmap_lo, fb, k * kBK, brow);
+            }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // =============================== MMA issuer =================================
+  } else if (warp == 1 && leader) {
+    // =============================== MMA issuer (pairs: leader CTA only) ========
     {
-      constexpr uint32_t idesc = make_idesc(BN);
+      constexpr uint32_t idesc = make_idesc(BN, kBM * CG);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t cc = 0;                                   // chunk counter (persists across tiles)
       long long t_wait_tempty = 0, t_wait_full = 0;
       const long long t_start = clock64();
-      for (int w = blockIdx.x; w < p.total_tiles * S; w += gridDim.x) {
+      for (int w = blockIdx.x / CG; w < p.total_tiles * S; w += gridDim.x / CG) {
         const int ks = w % S;
         const int kbeg = (ks * p.nkb) / S, kend = ((ks + 1) * p.nkb) / S;
         for (int k0 = kbeg; k0 < kend; k0 += G, ++cc) {
@@ -378,20 +450,31 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
 #pragma unroll
                 for (int kk = 0; kk < kBK / 16; ++kk) {
                   const uint64_t adv = (uint64_t)(kk * 2);  // 16 FP16 = 32 bytes = 2 descriptor units
-                  umma_f16(d, a_lo + adv, b_hi + adv, idesc, first);
-                  umma_f16(d, a_hi + adv, b_lo + adv, idesc, 1u);
+                  if (PAIR) {
+                    umma_f16_pair(d, a_lo + adv, b_hi + adv, idesc, first);
+                    umma_f16_pair(d, a_hi + adv, b_lo + adv, idesc, 1u);
+                  } else {
+                    umma_f16(d, a_lo + adv, b_hi + adv, idesc, first);
+                    umma_f16(d, a_hi + adv, b_lo + adv, idesc, 1u);
+                  }
                   first = 1u;
                 }
               }
 #pragma unroll
               for (int kk = 0; kk < kBK / 16; ++kk) {
                 const uint64_t adv = (uint64_t)(kk * 2);
-                umma_f16(d, a_hi + adv, b_hi + adv, idesc, first);
+                if (PAIR) umma_f16_pair(d, a_hi + adv, b_hi + adv, idesc, first);
+                else umma_f16(d, a_hi + adv, b_hi + adv, idesc, first);
                 first = 1u;
               }
             }
-            umma_commit(smem_u32(&empty_bar[stage]));   // frees the smem stage when these MMAs retire
-            if (k == k1 - 1) umma_commit(smem_u32(&tfull_bar[buf]));   // chunk complete -> accumulate warps
+            if (PAIR) {
+              umma_commit_pair(smem_u32(&empty_bar[stage]));                       // both CTAs' stages
+              if (k == k1 - 1) umma_commit_pair(smem_u32(&tfull_bar[buf]));        // both CTAs' accumulate warps
+            } else {
+              umma_commit(smem_u32(&empty_bar[stage]));   // frees the smem stage when these MMAs retire
+              if (k == k1 - 1) umma_commit(smem_u32(&tfull_bar[buf]));   // chunk complete -> accumulate warps
+            }
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -417,7 +500,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
     uint32_t cc = 0;
     int staged_key = -1;
     long long t_epi = 0, t_wait_tfull = 0, t_drain = 0;
-    for (int w = blockIdx.x; w < p.total_tiles * S; w += gridDim.x) {
+    for (int w = blockIdx.x / CG; w < p.total_tiles * S; w += gridDim.x / CG) {
       const int tile = w / S, ks = w - tile * S;
       const int kbeg = (ks * p.nkb) / S, kend = ((ks + 1) * p.nkb) / S;
       int r = tile;
@@ -425,12 +508,13 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       r /= p.n_tiles_n;
       const int cls = r % p.ncls;
       r /= p.ncls;
+      if (PAIR) r = 2 * r + (int)cta_rank;
       const int img = r / tiles_per_img;
       r -= img * tiles_per_img;
       const int r2 = r;
       const int y = (r / p.tiles_x) * (p.hbox * MT) + (MT == 2 ? half * p.hbox : 0) + (row >> p.wshift);
       const int x = (r % p.tiles_x) * p.wbox + (row & (p.wbox - 1));
-      const bool valid = y < p.Hl && x < p.Wl;
+      const bool valid = y < p.Hl && x < p.Wl && img < p.n_img;   // pairs: an odd tile count leaves one dummy tile
       const int n0 = nt * BN;
       // stage this tile's per-channel epilogue vectors -- only when they change (n-tile, or image when a
       // global-hints vector is added); for the single-n-tile layers that is once per kernel
@@ -491,7 +575,10 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+        if (lane == 0) {
+          if (PAIR && !leader) mbar_arrive_rank0(smem_u32(&tempty_bar[buf]));   // the leader's MMA warp owns the buffers
+          else mbar_arrive(smem_u32(&tempty_bar[buf]));
+        }
         if (IDC_CTA_COUNTERS && p.dbgbuf) t_drain += clock64() - tD;
       }
       const long long tE = (IDC_CTA_COUNTERS && p.dbgbuf) ? clock64() : 0;
@@ -551,7 +638,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       for (int i = 0; i < 4; ++i) {
         const int rr = quarter * 32 + i * 8 + (lane >> 2);
         const int yy = ty0 + (rr >> p.wshift), xx = tx0 + (rr & (p.wbox - 1));
-        tvalid[i] = yy < p.Hl && xx < p.Wl;
+        tvalid[i] = yy < p.Hl && xx < p.Wl && img < p.n_img;
         tbase[i] = ((size_t)(img * p.Hout + yy * p.os + (cls >> 1)) * p.Wout + xx * p.os + (cls & 1)) * p.Cout + n0 + c_base +
                    (lane & 3) * 8;
       }
@@ -674,11 +761,15 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
     p.dbgbuf[blockIdx.x * 8 + 5] = t_epi_g;
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // pairs: the peer may still arrive on / read from this CTA
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)SP::kTmemCols)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)SP::kTmemCols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)SP::kTmemCols)
+                   : "memory");
   }
 }
 
@@ -708,6 +799,7 @@ struct UmmaPlan {
   UmmaParams prm{};
   int num_sms = 148;
   int mt = 1;               // M-tiles (128 pixels each) per CTA tile
+  int cg = 1;               // 2: CTA pairs (cta_group::2), one 256x256 output tile per pair
   int split_k = 1;
   size_t ws_floats = 0;
   int ws_tiles = 0;
@@ -720,20 +812,29 @@ struct ViewKey {
 
 static int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
-template <int BN, int MT, bool SPLIT>
+template <int BN, int MT, int CG, bool SPLIT>
 static cudaError_t launch_inst(const UmmaPlan& pl, const UmmaParams& prm, cudaStream_t st) {
-  using SP = SmemPlan<BN, MT, SPLIT>;
+  using SP = SmemPlan<BN, MT, CG, SPLIT>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<BN, MT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<BN, MT, CG, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SP::kTotal);
     if (e != cudaSuccess) return e;
     attr = true;
   }
   const long items = (long)prm.total_tiles * prm.split_k;
-  const int grid = items < pl.num_sms ? (int)items : pl.num_sms;
-  umma_conv_kernel<BN, MT, SPLIT><<<grid, kThreads, SP::kTotal, st>>>(pl.bmap_hi, pl.bmap_lo, prm);
-  return cudaGetLastError();
+  int grid = items * CG < pl.num_sms ? (int)items * CG : (pl.num_sms / CG) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = SP::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = CG > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, umma_conv_kernel<BN, MT, CG, SPLIT>, pl.bmap_hi, pl.bmap_lo, prm);
 }
 
 int umma_plan_op(Ctx* c, ConvOp& op) {
@@ -764,6 +865,18 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
     if (tiles2 >= 2L * pl->num_sms && op.hbox * 2 <= 256) pl->mt = 2;
   }
   if (const char* e = getenv("IDC_MT")) { int v = atoi(e); if (v == 1 || (v == 2 && op.bn_tile <= 128)) pl->mt = v; }
+  // CTA pairs for the 256-wide tiles when the launch is large (never on the split-K / batch-1 path)
+  pl->cg = 1;
+  {
+    const long tiles1 = (long)op.ncls * c->max_n * ceil_div(op.Hl, op.hbox) * ceil_div(op.Wl, op.wbox) * (op.cout_pad / op.bn_tile);
+    const bool can = op.bn_tile == 256 && pl->mt == 1 && !c->fast;
+    bool pairs = false;    // IDC_PAIRS: unset/0 = off (opt-in until validated on hardware), 1 = large launches, 2 = always
+    if (const char* e = getenv("IDC_PAIRS")) {
+      const int v = atoi(e);
+      pairs = can && (v >= 2 || (v == 1 && tiles1 >= 2L * pl->num_sms));
+    }
+    if (pairs) pl->cg = 2;
+  }
   // views + k-block table
   std::vector<ViewKey> views;
   const int nkb = op.K / kBK;
@@ -819,7 +932,7 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   for (int part = 0; part < 2; ++part) {
     cuuint64_t dims[2] = {(cuuint64_t)op.K, (cuuint64_t)op.ncls * op.cout_pad};
     cuuint64_t strides[1] = {(cuuint64_t)op.K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)op.bn_tile};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)(op.bn_tile / pl->cg)};   // pairs: each CTA loads half of the weight tile
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(part == 0 ? &pl->bmap_hi : &pl->bmap_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                      part == 0 ? (void*)op.w_hi : (void*)op.w_lo, dims, strides, box, estr,
@@ -879,7 +992,7 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   {
     const long T = (long)op.ncls * c->max_n * q.tiles_y * q.tiles_x * q.n_tiles_n;
     int S = 1;
-    if (T * 2 <= pl->num_sms && nkb >= 8 && !op.fuse_out_head && pl->mt == 1) {
+    if (T * 2 <= pl->num_sms && nkb >= 8 && !op.fuse_out_head && pl->mt == 1 && pl->cg == 1) {
       S = (int)(pl->num_sms / T);
       if (S > nkb / 4) S = nkb / 4;
       if (S > op.bn_tile / 32) S = op.bn_tile / 32;      // one 32-column piece per CTA at least
@@ -912,7 +1025,8 @@ cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float ou
   if (!pl) return cudaErrorInvalidValue;
   UmmaParams prm = pl->prm;
   prm.n_img = n;
-  prm.total_tiles = op.ncls * n * prm.tiles_y * prm.tiles_x * prm.n_tiles_n;
+  const int m_tiles = n * prm.tiles_y * prm.tiles_x;
+  prm.total_tiles = op.ncls * (pl->cg == 2 ? (m_tiles + 1) / 2 : m_tiles) * prm.n_tiles_n;
   prm.gadd = (op.epi.gadd && c->gadd_active) ? c->gvec : nullptr;
   prm.out_ab = out_ab_fused;
   prm.dbgbuf = c->dbgbuf;
@@ -924,15 +1038,16 @@ cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float ou
   if (op.fuse_out_head && !out_ab_fused) return cudaErrorInvalidValue;
   c->launch_count++;
   const bool split = !c->fast;
-#define IDC_LAUNCH(BN_, MT_)                                                   \
-  return split ? launch_inst<BN_, MT_, true>(*pl, prm, st) : launch_inst<BN_, MT_, false>(*pl, prm, st)
-  switch (op.bn_tile * 10 + pl->mt) {
-    case 641: IDC_LAUNCH(64, 1);
-    case 642: IDC_LAUNCH(64, 2);
-    case 1281: IDC_LAUNCH(128, 1);
-    case 1282: IDC_LAUNCH(128, 2);
-    case 1921: IDC_LAUNCH(192, 1);
-    case 2561: IDC_LAUNCH(256, 1);
+#define IDC_LAUNCH(BN_, MT_, CG_)                                              \
+  return split ? launch_inst<BN_, MT_, CG_, true>(*pl, prm, st) : launch_inst<BN_, MT_, CG_, false>(*pl, prm, st)
+  switch (op.bn_tile * 100 + pl->mt * 10 + pl->cg) {
+    case 6411: IDC_LAUNCH(64, 1, 1);
+    case 6421: IDC_LAUNCH(64, 2, 1);
+    case 12811: IDC_LAUNCH(128, 1, 1);
+    case 12821: IDC_LAUNCH(128, 2, 1);
+    case 19211: IDC_LAUNCH(192, 1, 1);
+    case 25611: IDC_LAUNCH(256, 1, 1);
+    case 25612: IDC_LAUNCH(256, 1, 2);
     default: return cudaErrorInvalidValue;
   }
 #undef IDC_LAUNCH

@@ -10,18 +10,19 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=[1, 2], ids=["mt1", "mt2"])
+@pytest.fixture(scope="module", params=[(1, 0), (2, 0), (1, 2)], ids=["mt1", "mt2", "pairs"])
 def setup(request, synth_sd):
-    """mt = M-tiles per CTA tile (IDC_MT is read when the launch plan is built): both the 128-pixel
-    and the 256-pixel tile paths are exercised on every op that supports them."""
+    """(IDC_MT, IDC_PAIRS) are read when the launch plan is built: the 128-pixel tiles, the 256-pixel
+    tiles and the cta_group::2 pair path (forced, incl. the odd-tile-count dummy tile) are exercised on
+    every op that supports them."""
     import os
     L, ab, m = util.small_batch(3, 64, seed=300)
     _, inter = util.oracle_forward(synth_sd, L, ab, m, 0.5, dist=False, intermediates=True)
-    os.environ["IDC_MT"] = str(request.param)
+    os.environ["IDC_MT"], os.environ["IDC_PAIRS"] = str(request.param[0]), str(request.param[1])
     try:
         ctx = util.make_ctx(synth_sd, 64, 64, max_n=3, engine="tcgen05", keep_conv10=True, use_graph=False)
     finally:
-        del os.environ["IDC_MT"]
+        del os.environ["IDC_MT"], os.environ["IDC_PAIRS"]
     yield ctx, inter
     ctx.close()
 
