@@ -281,7 +281,7 @@ struct SmemPlan {
   static constexpr int kTmemCols = (kNBuf * kBufCols <= 128) ? 128 : (kNBuf * kBufCols <= 256 ? 256 : 512);
   static constexpr int kCH = (MT == 2) ? BN : BN / 2;            // accumulator columns per accumulate thread
   static_assert(kStages >= 2, "need at least a double-buffered operand ring");
-  static_assert(CG == 1 || (MT == 1 && BN == 256), "pairs are implemented for the 128x256 tile");
+  static_assert(CG == 1 || BN == 256 || BN == 128 || BN == 64, "pairs: BN/2 weight rows per CTA must be a whole number of swizzle atoms");
 };
 
 // ------------------------------------------------------------------------------------------
@@ -869,13 +869,11 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   pl->cg = 1;
   {
     const long tiles1 = (long)op.ncls * c->max_n * ceil_div(op.Hl, op.hbox) * ceil_div(op.Wl, op.wbox) * (op.cout_pad / op.bn_tile);
-    const bool can = op.bn_tile == 256 && pl->mt == 1 && !c->fast;
-    bool pairs = false;    // IDC_PAIRS: unset/0 = off (opt-in until validated on hardware), 1 = large launches, 2 = always
-    if (const char* e = getenv("IDC_PAIRS")) {
-      const int v = atoi(e);
-      pairs = can && (v >= 2 || (v == 1 && tiles1 >= 2L * pl->num_sms));
-    }
-    if (pairs) pl->cg = 2;
+    const bool can = !c->fast && (op.bn_tile == 256 || op.bn_tile == 128 || (op.bn_tile == 64 && pl->mt == 2));
+    const long tiles_mt = tiles1 / pl->mt;
+    int mode = 1;          // IDC_PAIRS: 0 = off, 1 (default) = launches that give every SM pair >= 2 tiles, 2 = always
+    if (const char* e = getenv("IDC_PAIRS")) mode = atoi(e);
+    if (can && (mode >= 2 || (mode == 1 && tiles_mt >= 4L * pl->num_sms))) pl->cg = 2;
   }
   // views + k-block table
   std::vector<ViewKey> views;
@@ -1048,6 +1046,9 @@ cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float ou
     case 19211: IDC_LAUNCH(192, 1, 1);
     case 25611: IDC_LAUNCH(256, 1, 1);
     case 25612: IDC_LAUNCH(256, 1, 2);
+    case 12812: IDC_LAUNCH(128, 1, 2);
+    case 12822: IDC_LAUNCH(128, 2, 2);
+    case 6422: IDC_LAUNCH(64, 2, 2);
     default: return cudaErrorInvalidValue;
   }
 #undef IDC_LAUNCH

@@ -10,7 +10,7 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=[(1, 0), (2, 0), (1, 2)], ids=["mt1", "mt2", "pairs"])
+@pytest.fixture(scope="module", params=[(1, 0), (2, 0), (1, 2), (2, 2)], ids=["mt1", "mt2", "pairs", "pairs_mt2"])
 def setup(request, synth_sd):
     """(IDC_MT, IDC_PAIRS) are read when the launch plan is built: the 128-pixel tiles, the 256-pixel
     tiles and the cta_group::2 pair path (forced, incl. the odd-tile-count dummy tile) are exercised on
