@@ -32,6 +32,25 @@ X = 256
 PER_GPU_BATCH = 64
 
 
+def _ncu_traffic(batch, size):
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this same workload (profiles/r01_ncu_full_umma_conv_batch64.csv)."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_full_umma_conv_batch64.csv")
+    if batch != 64 or size != 256 or not os.path.isfile(p):
+        return None
+    tot, n = 0.0, 0
+    for line in open(p):
+        if line.startswith("#") or line.startswith("op,"):
+            continue
+        f = line.strip().split('",')
+        if len(f) < 2:
+            continue
+        v = f[1].split(",")
+        tot += (float(v[2]) + float(v[3])) * 1e9          # dram_read[Gbyte], dram_write[Gbyte]
+        n += 1
+    return tot / n if n else None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -257,7 +276,8 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "umma_conv_kernel<BN,SPLIT> (tcgen05 implicit-GEMM conv, %d launches/step)" % n_launch,
                 "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor"],
                 "issued_mma_frac": split * achieved / peaks["tensor"],
-                "peak_source": peaks["src"], "traffic": None,
+                "peak_source": peaks["src"], "traffic": _ncu_traffic(N, X),
+                "traffic_note": "average DRAM bytes per umma_conv launch (ncu --set full, profiles/r01_ncu_full_umma_conv_batch64.csv)",
                 "algorithmic_flops_per_launch": conv_flops / max(n_launch, 1),
                 "avg_launch_ms": conv_ms / max(n_launch, 1),
                 "kernel_share_of_step": conv_ms / ms_step,

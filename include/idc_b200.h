@@ -143,6 +143,11 @@ int idc_lab2rgb_u8(int device, int n, int h, int w, const float* L, const float*
  * idc_zoom_lab2rgb_u8:  get_img_fullres (:123-131): scipy.ndimage.zoom(order=1) of ab [2,h_in,w_in] to
  *                       [h,w], then lab2rgb_transpose with the full-resolution L [h,w] -> uint8 [h,w,3]. */
 int idc_rgb2lab_f64(int device, int n, int h, int w, const uint8_t* rgb, double* lab, void* stream);
+/* f3: global statistics of a reference image (models/global_model/global_stats.prototxt:1-244; NNEncLayer with
+ * NN=1, caffe_files/caffe_traininglayers.py:161-196; usage DemoGlobalHistogramTransfer.ipynb:176-182):
+ * uint8 RGB [h,w,3] (h,w multiples of 4) + the 313 ab bin centres [313,2] -> out[316] =
+ * [313-bin histogram of the 4x4-pooled ab, 1, mean HSV saturation, 1] = the `glob` input of idc_forward. DEVICE ptrs. */
+int idc_global_stats(int device, int h, int w, const uint8_t* rgb, const float* pts313, float* out316, void* stream);
 int idc_zoom_lab2rgb_u8(int device, int h_in, int w_in, const double* ab, int h, int w, const double* L_full,
                         uint8_t* rgb, void* stream);
 

@@ -14,4 +14,5 @@ the package does not load it, the first network call does -- and raises if it is
 __version__ = "0.1.0"
 
 from .colorize_image import (ColorizeImageBase, ColorizeImageB200, ColorizeImageB200Dist,  # noqa: F401
+                             ColorizeImageB200GlobDist,
                              put_point, lab2rgb_transpose, rgb2lab_transpose)

@@ -321,3 +321,50 @@ class ColorizeImageB200Dist(ColorizeImageB200):
     def compute_entropy(self):
         d = np.asarray(self.dist_ab)
         self.dist_entropy = np.sum(d * np.log(d), axis=0)
+
+
+class ColorizeImageB200GlobDist(ColorizeImageB200):
+    """<-> ColorizeImageCaffeGlobDist (reference :445-463): colorization conditioned on a global ab histogram.
+    The global-hints branch of models/global_model/deploy_nodist.prototxt:38-172,501-527 is bolted onto the
+    local-hints network (a superset of the Caffe global model, whose conv1_1 ignores the local hints); its
+    weights arrive as extra state_dict keys `glob.{0..3}.*` (include/idc_b200.h).  Spec-only: no reference
+    weights or vectors exist for it offline."""
+
+    def __init__(self, Xd=256, maskcent=False, engine="tcgen05"):
+        ColorizeImageB200.__init__(self, Xd, maskcent=maskcent, engine=engine)
+        self.glob_mask_mult = 1.
+
+    def prep_net(self, gpu_id=None, path='', state_dict=None):
+        import torch
+        from .engine import LhnContext
+        if state_dict is None:
+            state_dict = torch.load(path, map_location='cpu')
+        self._ctx = LhnContext(device=0 if gpu_id is None else int(gpu_id), max_n=1, H=self.Xd, W=self.Xd,
+                               engine=self.engine, global_hints=True)
+        self._ctx.load_state_dict(state_dict)
+        self.net_set = True
+
+    def get_global_histogram(self, ref_rgb_u8):
+        """DemoGlobalHistogramTransfer.ipynb:176-182: the reference image is resized to Xd x Xd, then
+        global_stats.prototxt -> the first 313 entries are `glob_dist`."""
+        import cv2
+        from . import prepost
+        img = cv2.resize(ref_rgb_u8, (self.Xd, self.Xd))
+        self.glob_vec = prepost.global_stats_gpu(img, self._ctx.device)
+        return self.glob_vec[:313].copy()
+
+    def net_forward(self, input_ab, input_mask, glob_dist=-1):
+        if ColorizeImageBase.net_forward(self, input_ab, input_mask) == -1:
+            return -1
+        glob = np.zeros((1, 316), np.float32)            # "run without this, zero it out" (reference :454-456)
+        if np.array(glob_dist).flatten()[0] != -1:
+            glob[0, :313] = np.asarray(glob_dist, dtype=np.float32)
+            glob[0, 313] = self.glob_mask_mult             # reference :458-459; the s_avg input stays 0 as in the reference
+        A = np.ascontiguousarray(self.img_l_mc, dtype=np.float32)[None]
+        B = np.ascontiguousarray(self.input_ab_mc, dtype=np.float32)[None]
+        M = np.ascontiguousarray(self.input_mask_mult, dtype=np.float32)[None]
+        r = self._ctx.forward_host(A, B, M, float(self.mask_cent), glob=glob, want_rgb=True)
+        self.output_ab_raw = r["ab"][0]
+        self.output_rgb = r["rgb"][0]
+        ColorizeImageBase._set_out_ab_(self)
+        return self.output_rgb

@@ -783,6 +783,12 @@ int idc_lab2rgb_u8(int device, int n, int h, int w, const float* L, const float*
   return launch_lab2rgb(n, h, w, L, 0.0f, ab, rgb, (cudaStream_t)stream) == cudaSuccess ? IDC_OK : IDC_ERR_CUDA;
 }
 
+int idc_global_stats(int device, int h, int w, const uint8_t* rgb, const float* pts313, float* out316, void* stream) {
+  if (h < 4 || w < 4 || (h % 4) || (w % 4) || !rgb || !pts313 || !out316) return IDC_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return IDC_ERR_CUDA;
+  return launch_global_stats(h, w, rgb, pts313, out316, (cudaStream_t)stream) == cudaSuccess ? IDC_OK : IDC_ERR_CUDA;
+}
+
 int idc_rgb2lab_f64(int device, int n, int h, int w, const uint8_t* rgb, double* lab, void* stream) {
   if (n < 1 || h < 1 || w < 1 || !rgb || !lab) return IDC_ERR_ARG;
   if (cudaSetDevice(device) != cudaSuccess) return IDC_ERR_CUDA;

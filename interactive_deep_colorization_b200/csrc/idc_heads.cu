@@ -334,6 +334,76 @@ __global__ void zoom_lab2rgb_kernel(const double* __restrict__ ab, int hin, int 
   lab_to_rgb_u8(Lfull[i], v[0], v[1], rgb + i * 3);
 }
 
+// ------------------------------------------------------------------------------------------
+// f3: global statistics of a reference image = the glob vector of BASELINE config 4
+// (models/global_model/global_stats.prototxt: BGR2Lab -> 4x4 average pool of ab -> NNEncLayer with NN=1,
+//  sigma=5 (caffe_files/caffe_traininglayers.py:161-196: hard assignment to the nearest of the 313 bins) ->
+//  global average = histogram; BGR2HSV -> global average of S).  One thread per pooled 4x4 cell.
+//  out[316] = [313 histogram, 1, mean saturation, 1]   (indicators as data/colorize_image.py:452-463 sets them)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) global_stats_kernel(const uint8_t* __restrict__ rgb, int H, int W,
+                                                           const float* __restrict__ pts, float* __restrict__ out) {
+  __shared__ int hist[313];
+  __shared__ double ssum[8];
+  for (int i = threadIdx.x; i < 313; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const int H4 = H / 4, W4 = W / 4;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  double sat = 0.0;
+  if (cell < H4 * W4) {
+    const int cy = cell / W4, cx = cell - cy * W4;
+    double sa = 0.0, sb = 0.0;
+    for (int dy = 0; dy < 4; ++dy)
+      for (int dx = 0; dx < 4; ++dx) {
+        const uint8_t* px = rgb + ((size_t)(cy * 4 + dy) * W + (cx * 4 + dx)) * 3;
+        const double r8 = px[0] / 255.0, g8 = px[1] / 255.0, b8 = px[2] / 255.0;
+        const double R = srgb_inv_gamma(r8), G = srgb_inv_gamma(g8), B = srgb_inv_gamma(b8);
+        const double X = (0.412453 * R + 0.357580 * G + 0.180423 * B) / 0.95047;
+        const double Y = (0.212671 * R + 0.715160 * G + 0.072169 * B);
+        const double Z = (0.019334 * R + 0.119193 * G + 0.950227 * B) / 1.08883;
+        const double fx = lab_f(X), fy = lab_f(Y), fz = lab_f(Z);
+        sa += 500.0 * (fx - fy);
+        sb += 200.0 * (fy - fz);
+        const double mx = fmax(r8, fmax(g8, b8)), mn = fmin(r8, fmin(g8, b8));
+        sat += mx > 0.0 ? (mx - mn) / mx : 0.0;            // skimage rgb2hsv saturation
+      }
+    const float a = (float)(sa / 16.0), b = (float)(sb / 16.0);
+    int best = 0;
+    float bd = 3.4e38f;
+    for (int k = 0; k < 313; ++k) {
+      const float da = a - pts[2 * k], db = b - pts[2 * k + 1];
+      const float d = da * da + db * db;
+      if (d < bd) { bd = d; best = k; }
+    }
+    atomicAdd(&hist[best], 1);
+  }
+  // block reduction of the saturation sum (fixed order inside the block)
+  for (int o = 16; o > 0; o >>= 1) sat += __shfl_xor_sync(0xffffffffu, sat, o);
+  if ((threadIdx.x & 31) == 0) ssum[threadIdx.x >> 5] = sat;
+  __syncthreads();
+  const float inv_cells = 1.0f / (float)(H4 * W4);
+  for (int i = threadIdx.x; i < 313; i += blockDim.x)
+    if (hist[i]) atomicAdd(out + i, hist[i] * inv_cells);
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += ssum[i];
+    atomicAdd(out + 314, (float)(t / ((double)H * W)));
+  }
+}
+
+cudaError_t launch_global_stats(int h, int w, const uint8_t* rgb, const float* pts, float* out316, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(out316, 0, 316 * sizeof(float), st);
+  if (e != cudaSuccess) return e;
+  const int cells = (h / 4) * (w / 4);
+  global_stats_kernel<<<(cells + 255) / 256, 256, 0, st>>>(rgb, h, w, pts, out316);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const float one = 1.0f;
+  e = cudaMemcpyAsync(out316 + 313, &one, sizeof(float), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyAsync(out316 + 315, &one, sizeof(float), cudaMemcpyHostToDevice, st);
+}
+
 cudaError_t launch_rgb2lab(int n, int h, int w, const uint8_t* rgb, double* lab, cudaStream_t st) {
   const size_t tot = (size_t)n * h * w;
   rgb2lab_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(rgb, n, h * w, lab);

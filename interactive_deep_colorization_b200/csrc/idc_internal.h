@@ -187,6 +187,7 @@ cudaError_t launch_lab2rgb(int n, int h, int w, const float* L, float l_offset, 
                            uint8_t* rgb, cudaStream_t st);
 cudaError_t launch_decode313(Ctx* c, int n, float T, float* out_ab, cudaStream_t st);
 cudaError_t launch_dist313_pixel(Ctx* c, int img, int y, int x, float S, float* out313_dev, cudaStream_t st);
+cudaError_t launch_global_stats(int h, int w, const uint8_t* rgb, const float* pts, float* out316, cudaStream_t st);
 cudaError_t launch_rgb2lab(int n, int h, int w, const uint8_t* rgb, double* lab, cudaStream_t st);
 cudaError_t launch_zoom_lab2rgb(const double* ab, int hin, int win, const double* Lfull, int H, int W, uint8_t* rgb,
                                 cudaStream_t st);

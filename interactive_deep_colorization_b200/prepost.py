@@ -49,3 +49,25 @@ def fullres_rgb_gpu(ab, l_fullres, device=0):
     if rc != _lib.IDC_OK:
         raise _lib.IdcError(rc, "idc_zoom_lab2rgb_u8 failed")
     return d_rgb.cpu().numpy()
+
+
+def pts_in_hull():
+    """The 313 in-gamut ab bin centres (data fixture of the reference: data/color_bins/pts_in_hull.npy)."""
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "pts_in_hull.npy")).astype(np.float32)
+
+
+def global_stats_gpu(rgb_u8, device=0):
+    """Reference image uint8 [H,W,3] (H, W multiples of 4) -> glob vector [316] =
+    [313-bin ab histogram, 1, mean saturation, 1] (row f3; global_stats.prototxt)."""
+    torch = _torch()
+    a = np.ascontiguousarray(rgb_u8)
+    assert a.dtype == np.uint8 and a.ndim == 3 and a.shape[2] == 3
+    d_rgb = torch.from_numpy(a).to("cuda:%d" % device)
+    d_pts = torch.from_numpy(pts_in_hull()).to(d_rgb.device)
+    d_out = torch.empty((316,), dtype=torch.float32, device=d_rgb.device)
+    st = torch.cuda.current_stream(d_rgb.device).cuda_stream
+    rc = _lib.load().idc_global_stats(device, a.shape[0], a.shape[1], d_rgb.data_ptr(), d_pts.data_ptr(), d_out.data_ptr(), st)
+    if rc != _lib.IDC_OK:
+        raise _lib.IdcError(rc, "idc_global_stats failed")
+    return d_out.cpu().numpy()

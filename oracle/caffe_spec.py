@@ -89,3 +89,20 @@ def caffe313_head(csd, inter, T=2.6, S=0.2, return_logits=False):
     if return_logits:
         return pred_ab, dist_S, logits, h
     return pred_ab, dist_S
+
+
+def global_stats(rgb_u8, pts_in_hull):
+    """numpy restatement of models/global_model/global_stats.prototxt for one uint8 RGB image:
+    Lab (skimage, oracle/color_ref.py) -> 4x4 average pool of ab -> NNEncLayer (NN=1: nearest bin) ->
+    global average; mean HSV saturation.  -> [313 hist, 1, s_avg, 1].  PARITY UNPINNED."""
+    from . import color_ref
+    lab = color_ref.rgb2lab(rgb_u8)
+    H, W = lab.shape[:2]
+    ab = lab[..., 1:].reshape(H // 4, 4, W // 4, 4, 2).mean(axis=(1, 3)).reshape(-1, 2).astype(np.float32)
+    pts = np.asarray(pts_in_hull, dtype=np.float32)
+    d = ((ab[:, None, :] - pts[None, :, :]) ** 2).sum(-1)
+    hist = np.bincount(d.argmin(1), minlength=313).astype(np.float64) / ab.shape[0]
+    c = rgb_u8.astype(np.float64) / 255.0
+    mx, mn = c.max(-1), c.min(-1)
+    s = np.where(mx > 0, (mx - mn) / np.where(mx > 0, mx, 1.0), 0.0)
+    return np.concatenate([hist, [1.0], [s.mean()], [1.0]]).astype(np.float32)

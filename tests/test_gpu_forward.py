@@ -251,3 +251,44 @@ def test_prepost_gpu_kernels_match_numpy_scipy():
     ref = color_ref.lab2rgb_transpose(Lf, zoom(ab, (1, 75 / 32., 91 / 32.), order=1))
     d = np.abs(got.astype(int) - ref.astype(int))
     assert d.max() <= 1 and (d > 0).mean() < 1e-3, (d.max(), (d > 0).mean())
+
+
+def test_global_stats_kernel():
+    """row f3: histogram / saturation extractor against the numpy restatement of global_stats.prototxt."""
+    from oracle import caffe_spec
+    from interactive_deep_colorization_b200 import prepost
+    g = util.golden("lhn_256.npz")
+    pts = np.load(util.os.path.join(util.GOLDEN, "pts_in_hull.npy"))
+    assert np.array_equal(pts, prepost.pts_in_hull())
+    for rgb in (g["img_rgb"], np.random.RandomState(2).randint(0, 256, (64, 96, 3)).astype(np.uint8)):
+        got = prepost.global_stats_gpu(rgb)
+        ref = caffe_spec.global_stats(rgb, pts)
+        assert got.shape == (316,) and abs(got[:313].sum() - 1.0) < 1e-5
+        assert np.abs(got - ref).max() < 2e-3, np.abs(got - ref).max()      # a cell on a bin boundary may flip
+        assert np.abs(got[313:] - ref[313:]).max() < 1e-6
+
+
+def test_globdist_wrapper(synth_sd):
+    """ColorizeImageB200GlobDist used like the reference notebook uses ColorizeImageCaffeGlobDist."""
+    from interactive_deep_colorization_b200 import colorize_image as CI
+    from oracle import caffe_spec
+    gsd = caffe_spec.synthetic_glob_state_dict()
+    sd = dict(synth_sd)
+    sd.update({k: torch.from_numpy(v) for k, v in gsd.items()})
+    g = util.golden("lhn_256.npz")
+    cid = CI.ColorizeImageB200GlobDist(Xd=256)
+    cid.prep_net(state_dict=sd)
+    cid.set_image(g["img_rgb"])
+    ab, m = np.zeros((2, 256, 256)), np.zeros((1, 256, 256))
+    plain = cid.net_forward(ab, m)                                  # glob_dist = -1 -> zeros
+    raw_plain = cid.output_ab_raw.copy()
+    ref_rgb = np.random.RandomState(4).randint(0, 256, (120, 160, 3)).astype(np.uint8)
+    hist = cid.get_global_histogram(ref_rgb)
+    assert hist.shape == (313,) and abs(hist.sum() - 1) < 1e-5
+    out = cid.net_forward(ab, m, hist)
+    assert out.shape == (256, 256, 3) and plain.shape == (256, 256, 3)
+    glob = np.zeros((1, 316), np.float32); glob[0, :313] = hist; glob[0, 313] = 1
+    L = g["img_l_mc"].astype(np.float32)[None]
+    for gl, got in ((np.zeros((1, 316), np.float32), raw_plain), (glob, cid.output_ab_raw)):
+        ref = util.oracle_forward(synth_sd, L, ab[None], m[None], 0.0, glob_add=caffe_spec.global_hints_vector(gsd, gl))
+        assert util.maxabs(got, ref[0]) <= TOL_AB
