@@ -124,7 +124,6 @@ struct Ctx {
   char* arena = nullptr;
   size_t arena_bytes = 0;
   bool weights_ready = false;
-  bool arena_laid_out = false;
   // conv1_1 (4->64) + regression head + misc small weights (device fp32)
   float* w11 = nullptr;   // [36][64]  k = tap*4 + cin
   float* b11 = nullptr;   // [64]
@@ -143,7 +142,6 @@ struct Ctx {
   float* logits313 = nullptr;  // Caffe-spec head: [max_n*(H/4)*(W/4)][320]
   bool caffe313 = false;
   float* pts313 = nullptr;     // [313][2] ab bin centres (device)
-  float* conv10_f32 = nullptr; // SIMT: conv10_2 is a normal buffer; unused otherwise
   // split-K workspace of the tcgen05 engine (sized by umma_plan_op, allocated after planning)
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;
   int* splitk_counters = nullptr; int splitk_max_tiles = 0;
@@ -157,7 +155,6 @@ struct Ctx {
   cudaStream_t own_stream = nullptr;
   // CUDA graph cache for the batch-1 latency path
   cudaGraphExec_t graph_exec = nullptr;
-  int graph_n = 0;
   const void* graph_ptrs[8] = {nullptr};
   float graph_maskcent = 0.f;
   int launch_count = 0;
