@@ -631,6 +631,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         tbase[i] = ((size_t)(img * p.Hout + yy * p.os + (cls >> 1)) * p.Wout + xx * p.os + (cls & 1)) * p.Cout + n0 + c_base +
                    (lane & 3) * 8;
       }
+      const float neg_slope = p.act == ACT_RELU ? 0.f : (p.act == ACT_LEAKY02 ? 0.2f : 1.f);
       float h0 = 0.f, h1 = 0.f;
 #pragma unroll
       for (int ch = 0; ch < CH; ch += 32) {
@@ -644,10 +645,10 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           const float b4[4] = {vb.x, vb.y, vb.z, vb.w}, s4[4] = {vs.x, vs.y, vs.z, vs.w}, t4[4] = {vt.x, vt.y, vt.z, vt.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float t = acc[ch + j4 + j] + b4[j];
-            if (p.act == ACT_RELU) t = fmaxf(t, 0.f);
-            else if (p.act == ACT_LEAKY02) t = t > 0.f ? t : 0.2f * t;
-            f[j4 + j] = fmaf(t, s4[j], t4[j]);
+            // one branch-free form for none / ReLU / LeakyReLU(0.2): max(t,0) + slope*min(t,0), slope = 1 / 0 / 0.2
+            const float t = acc[ch + j4 + j] + b4[j];
+            const float a = fmaf(neg_slope, fminf(t, 0.f), fmaxf(t, 0.f));
+            f[j4 + j] = fmaf(a, s4[j], t4[j]);
           }
         }
         if (p.wout) {
