@@ -292,3 +292,28 @@ def test_globdist_wrapper(synth_sd):
     for gl, got in ((np.zeros((1, 316), np.float32), raw_plain), (glob, cid.output_ab_raw)):
         ref = util.oracle_forward(synth_sd, L, ab[None], m[None], 0.0, glob_add=caffe_spec.global_hints_vector(gsd, gl))
         assert util.maxabs(got, ref[0]) <= TOL_AB
+
+
+@pytest.mark.parametrize("H,W,n", [(72, 88, 2), (128, 64, 3), (8, 8, 1)])
+def test_odd_geometries(synth_sd, H, W, n):
+    """Geometry is any multiple of 8 (three ::2 + three x2 stages): partial tiles, non-square images, tile
+    counts that do not pair up, and the smallest legal size."""
+    rs = np.random.RandomState(H * 1000 + W)
+    L = (rs.rand(n, 1, H, W) * 100 - 50).astype(np.float32)
+    ab = np.zeros((n, 2, H, W), np.float32)
+    m = np.zeros((n, 1, H, W), np.float32)
+    for i in range(n):
+        y, x = rs.randint(0, H - 3), rs.randint(0, W - 3)
+        ab[i, :, y:y + 3, x:x + 3] = rs.uniform(-80, 80, (2, 1, 1))
+        m[i, :, y:y + 3, x:x + 3] = 1
+    ref = util.oracle_forward(synth_sd, L, ab, m, 0.5, dist=True)
+    for forced_pairs in ("0", "2"):
+        util.os.environ["IDC_PAIRS"] = forced_pairs
+        try:
+            ctx = util.make_ctx(synth_sd, H, W, max_n=n, dist=True)
+        finally:
+            del util.os.environ["IDC_PAIRS"]
+        r = ctx.forward_host(L, ab, m, 0.5, want_dist=True, want_rgb=True)
+        assert util.maxabs(r["ab"], ref[0]) <= TOL_AB, (H, W, forced_pairs)
+        assert util.maxabs(r["dist"], ref[1]) < 1e-5
+        ctx.close()
