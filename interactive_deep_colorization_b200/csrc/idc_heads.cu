@@ -40,9 +40,10 @@ __global__ void __launch_bounds__(128) conv1_1_kernel(const __grid_constant__ Co
                                                       __half* __restrict__ olo) {
   const size_t HW = (size_t)H * Wd;
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= (size_t)N * HW) return;
-  const int n = (int)(pix / HW);
-  const int r = (int)(pix - (size_t)n * HW);
+  const bool live = pix < (size_t)N * HW;                   // N*HW is a multiple of 64, blocks are 128 wide
+  const size_t pixc = live ? pix : 0;
+  const int n = (int)(pixc / HW);
+  const int r = (int)(pixc - (size_t)n * HW);
   const int y = r / Wd, x = r - y * Wd;
   float in[36];
 #pragma unroll
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(128) conv1_1_kernel(const __grid_constant__ Co
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
       const int iy = y + ky - 1, ix = x + kx - 1;
-      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < Wd;
+      const bool ok = live && iy >= 0 && iy < H && ix >= 0 && ix < Wd;
       const size_t o = (size_t)iy * Wd + ix;
       const int t = (ky * 3 + kx) * 4;
       // zero padding applies to the concatenated, normalised input (model.py:148 then Conv2d pad)
@@ -70,20 +71,41 @@ __global__ void __launch_bounds__(128) conv1_1_kernel(const __grid_constant__ Co
 #pragma unroll
   for (int c = 0; c < 64; ++c) acc[c] = fmaxf(acc[c], 0.f);
   if (!SPLIT) {
+    if (!live) return;
     float4* op = reinterpret_cast<float4*>(outf + pix * 64);
 #pragma unroll
     for (int c4 = 0; c4 < 16; ++c4) op[c4] = make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
   } else {
-    uint4* oh = reinterpret_cast<uint4*>(ohi + pix * 64);
-    uint4* ol = reinterpret_cast<uint4*>(olo + pix * 64);
+    // The warp's 32 pixels x 64 channels are one contiguous 4 KB block per plane in NHWC.  Writing 16 bytes per
+    // lane at a 128-byte stride costs one L1 transaction per lane; instead transpose through a swizzled smem
+    // tile so every store instruction writes 512 contiguous bytes.
+    __shared__ __align__(16) uint4 tile[4][32 * 8];          // per warp: 32 rows x 8 chunks of 16 B
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t wpix0 = pix - lane;                          // first pixel of this warp (blocks are 128-aligned)
+    const size_t total = (size_t)N * HW;
 #pragma unroll
-    for (int c8 = 0; c8 < 8; ++c8) {
-      __align__(16) __half h[8];
-      __align__(16) __half l[8];
+    for (int plane = 0; plane < 2; ++plane) {
+      if (plane == 1 && !olo) break;                          // IDC_FLAG_FAST_FP16: no lo plane
 #pragma unroll
-      for (int j = 0; j < 8; ++j) split_half(acc[c8 * 8 + j] * kActScale, h[j], l[j]);
-      oh[c8] = *reinterpret_cast<uint4*>(h);
-      if (olo) ol[c8] = *reinterpret_cast<uint4*>(l);   // olo == null in IDC_FLAG_FAST_FP16 mode
+      for (int c8 = 0; c8 < 8; ++c8) {
+        __align__(16) __half h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          __half hi, lo;
+          split_half(acc[c8 * 8 + j] * kActScale, hi, lo);
+          h[j] = plane == 0 ? hi : lo;
+        }
+        tile[warp][lane * 8 + (c8 ^ (lane & 7))] = *reinterpret_cast<uint4*>(h);
+      }
+      __syncwarp();
+      __half* gbase = (plane == 0 ? ohi : olo) + wpix0 * 64;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rl = i * 4 + (lane >> 3), c = lane & 7;
+        if (wpix0 + rl < total)
+          reinterpret_cast<uint4*>(gbase)[i * 32 + lane] = tile[warp][rl * 8 + (c ^ (rl & 7))];
+      }
+      __syncwarp();
     }
   }
 }
