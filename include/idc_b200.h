@@ -119,6 +119,21 @@ int idc_forward_host(idc_ctx* ctx, int n, int h, int w, const float* L_mc, const
 int idc_set_dist_resident(idc_ctx* ctx, int on);
 int idc_fetch_dist(idc_ctx* ctx, int img, int y4, int x4, float* out_host);
 
+/* Colour suggestions at one pixel of the resident distribution (replaces
+ * ColorizeImageTorchDist.get_ab_reccs, data/colorize_image.py:322-354: 25 000 inverse-CDF samples of
+ * dist_ab[:, h, w] -> sklearn KMeans(K) -> centres ordered by occupancy).  Computed as the sample-size ->
+ * infinity limit of that procedure: deterministic weighted k-means over the 529 gamut points with the pmf
+ * as weights (seeds: heaviest bin, then argmax w*d^2; FP64 Lloyd iterations until the assignment is stable
+ * or max_iter); n_init restarts run side by side (restart v seeds from the bin of weight-rank v) and the one
+ * with the lowest inertia wins (sklearn's n_init; 1 <= n_init <= 16).  pts_host: [529][2] ab coordinates of the bins, or NULL for the PyTorch wrapper's grid
+ * (bin i = (g[i % 23], g[i / 23]), g = -110..110 step 10, :283).  Outputs (host): centers [K][2], conf [K]
+ * (cluster mass, descending; may be NULL), iters_out (Lloyd iterations used; may be NULL).  1 <= K <= 32. */
+int idc_ab_reccs(idc_ctx* ctx, int img, int y4, int x4, int K, int max_iter, int n_init, const float* pts_host,
+                 float* centers_host, float* conf_host, int* iters_out);
+/* Same clustering for a caller-supplied pmf (host, 529 floats, need not be normalised); no ctx needed. */
+int idc_ab_reccs_pmf(int device, const float* pmf_host, int K, int max_iter, int n_init, const float* pts_host,
+                     float* centers_host, float* conf_host, int* iters_out);
+
 /* Caffe-spec 313-bin head (models/reference_model/deploy_nopred.prototxt:651-850, weight
  * injection data/colorize_image.py:405-413).  With IDC_FLAG_CAFFE313 every forward also runs the
  * hyper-column (conv3_pred + conv4..7_pred + conv8_pred, ReLU) and pred_313 (1x1 -> 313 logits at h/4).

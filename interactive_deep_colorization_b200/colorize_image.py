@@ -297,16 +297,31 @@ class ColorizeImageB200Dist(ColorizeImageB200):
         else:
             self.dist_ab = _LazyUpsampledDist(fetch=lambda y4, x4: ctx.fetch_dist(0, y4, x4),
                                               shape64=(529, A.shape[-2] // 4, A.shape[-1] // 4))
+        self._dist_ctx = ctx
         self.dist_ab_set = True
         # reference returns the regression output scaled by 110 twice (model.py:166-168, q1)
         return self.output_ab_raw * 110.0
 
-    def get_ab_reccs(self, h, w, K=5, N=25000, return_conf=False):
-        """Colour suggestions at pixel (h, w) (reference :322-354): draw N samples from the
-        529-bin distribution by inverse-CDF lookup, k-means them, order clusters by mass."""
+    def get_ab_reccs(self, h, w, K=5, N=25000, return_conf=False, method='gpu'):
+        """Colour suggestions at pixel (h, w) (reference :322-354).  The reference draws N samples from the
+        529-bin distribution by inverse-CDF lookup, k-means them and orders the clusters by occupancy.
+        method='gpu' (default): the N -> infinity limit of that, weighted k-means on the device over the
+        resident distribution (idc_ab_reccs; deterministic, N unused).  method='sampled': the reference's
+        stochastic procedure on the host (np.random + sklearn), for side-by-side comparison."""
         if not self.dist_ab_set:
             print('Need to set prediction first')
             return 0
+        if method == 'gpu':
+            if not self.materialize_full:                    # the pixel's pmf never leaves the device
+                centers, conf, _ = self._dist_ctx.ab_reccs(0, int(h) // 4, int(w) // 4, K=K, pts=self.pts_in_hull)
+            else:
+                from .prepost import ab_reccs_pmf_gpu
+                centers, conf, _ = ab_reccs_pmf_gpu(np.asarray(self.dist_ab[:, h, w]), K=K, pts=self.pts_in_hull,
+                                                    device=self._dist_ctx.device)
+            centers, conf = centers.astype(np.float64), conf.astype(np.float64)
+            return (centers, conf) if return_conf else centers
+        if method != 'sampled':
+            raise ValueError("method must be 'gpu' or 'sampled'")
         from sklearn.cluster import KMeans
         cdf = np.cumsum(np.asarray(self.dist_ab[:, h, w]))
         cdf /= cdf[-1]

@@ -756,6 +756,73 @@ int idc_fetch_dist(idc_ctx* c, int img, int y4, int x4, float* out) {
   return IDC_OK;
 }
 
+// shared by idc_ab_reccs / idc_ab_reccs_pmf.  scratch (doubles): [kReccsMaxInit][3*32+2] results, then the 529x2
+// gamut points as floats.
+constexpr int kReccsMaxInit = 16, kReccsRes = 3 * 32 + 2;
+constexpr size_t kReccsScratchBytes = (size_t)kReccsMaxInit * kReccsRes * sizeof(double) + 529 * 2 * sizeof(float);
+
+static bool reccs_args_ok(int K, int max_iter, int n_init) {
+  return K >= 1 && K <= 32 && max_iter >= 1 && n_init >= 1 && n_init <= kReccsMaxInit;
+}
+
+static cudaError_t reccs_run(const float* pmf_dev, size_t bin_stride, double* scratch, int K, int max_iter, int n_init,
+                             const float* pts_host, float* centers_host, float* conf_host, int* iters_out) {
+  float pts[529 * 2];
+  if (pts_host) {
+    memcpy(pts, pts_host, sizeof(pts));
+  } else {   // the PyTorch wrapper's gamut grid (data/colorize_image.py:283, quirk q3): bin i = (g[i % 23], g[i / 23])
+    for (int i = 0; i < 529; ++i) { pts[2 * i] = -110.f + 10.f * (i % 23); pts[2 * i + 1] = -110.f + 10.f * (i / 23); }
+  }
+  float* pts_dev = reinterpret_cast<float*>(scratch + (size_t)kReccsMaxInit * kReccsRes);
+  cudaError_t e = cudaMemcpy(pts_dev, pts, sizeof(pts), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return e;
+  if ((e = launch_ab_reccs(pmf_dev, bin_stride, pts_dev, K, max_iter, n_init, scratch, 0)) != cudaSuccess) return e;
+  const int stride = 3 * K + 2;
+  double res[kReccsMaxInit * kReccsRes];
+  if ((e = cudaMemcpy(res, scratch, (size_t)n_init * stride * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+  // best restart = lowest inertia; restarts within 1e-9 (relative) of it count as ties -> lowest index
+  double best = res[stride - 1];
+  for (int v = 1; v < n_init; ++v) best = std::min(best, res[v * stride + stride - 1]);
+  int pick = 0;
+  while (res[pick * stride + stride - 1] > best * (1.0 + 1e-9) + 1e-300) ++pick;
+  const double* r = res + (size_t)pick * stride;
+  for (int i = 0; i < 2 * K; ++i) centers_host[i] = (float)r[i];
+  if (conf_host) for (int k = 0; k < K; ++k) conf_host[k] = (float)r[2 * K + k];
+  if (iters_out) *iters_out = (int)r[3 * K];
+  return cudaSuccess;
+}
+
+int idc_ab_reccs(idc_ctx* c, int img, int y4, int x4, int K, int max_iter, int n_init, const float* pts_host,
+                 float* centers_host, float* conf_host, int* iters_out) {
+  if (!c || !centers_host) return IDC_ERR_ARG;
+  if (!reccs_args_ok(K, max_iter, n_init))
+    return fail(c, IDC_ERR_ARG, "idc_ab_reccs: need 1 <= K <= 32, max_iter >= 1, 1 <= n_init <= %d", kReccsMaxInit);
+  if (img < 0 || img >= c->dist_valid_n || !c->d_out)
+    return fail(c, IDC_ERR_STATE, "no resident distribution for image %d (run idc_forward_host with resident mode on)", img);
+  const int H4 = c->H / 4, W4 = c->W / 4;
+  if (y4 < 0 || y4 >= H4 || x4 < 0 || x4 >= W4) return fail(c, IDC_ERR_ARG, "pixel (%d,%d) outside the %dx%d grid", y4, x4, H4, W4);
+  const size_t HW = (size_t)c->H * c->W, HW4 = (size_t)H4 * W4;
+  const float* d = c->d_out + (size_t)c->max_n * 2 * HW + (size_t)img * 529 * HW4 + (size_t)y4 * W4 + x4;
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  if (!c->d_reccs) CUDA_TRY(c, cudaMalloc(&c->d_reccs, kReccsScratchBytes));
+  CUDA_TRY(c, reccs_run(d, HW4, c->d_reccs, K, max_iter, n_init, pts_host, centers_host, conf_host, iters_out));
+  return IDC_OK;
+}
+
+int idc_ab_reccs_pmf(int device, const float* pmf_host, int K, int max_iter, int n_init, const float* pts_host,
+                     float* centers_host, float* conf_host, int* iters_out) {
+  if (!pmf_host || !centers_host || !reccs_args_ok(K, max_iter, n_init)) return IDC_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return IDC_ERR_CUDA;
+  char* buf = nullptr;
+  if (cudaMalloc(&buf, kReccsScratchBytes + 529 * sizeof(float)) != cudaSuccess) return IDC_ERR_CUDA;
+  float* pmf_dev = reinterpret_cast<float*>(buf + kReccsScratchBytes);
+  cudaError_t e = cudaMemcpy(pmf_dev, pmf_host, 529 * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = reccs_run(pmf_dev, 1, reinterpret_cast<double*>(buf), K, max_iter, n_init, pts_host, centers_host, conf_host, iters_out);
+  cudaFree(buf);
+  return e == cudaSuccess ? IDC_OK : IDC_ERR_CUDA;
+}
+
 int idc_caffe313_pred_ab(idc_ctx* c, int n, float T, float* out_ab, void* stream) {
   if (!c || !out_ab || n < 1 || n > c->max_n) return IDC_ERR_ARG;
   if (!c->caffe313) return fail(c, IDC_ERR_STATE, "ctx was not created with IDC_FLAG_CAFFE313");
@@ -926,6 +993,7 @@ int idc_destroy(idc_ctx* c) {
   if (c->pts313) cudaFree(c->pts313);
   if (c->splitk_ws) cudaFree(c->splitk_ws);
   if (c->splitk_counters) cudaFree(c->splitk_counters);
+  if (c->d_reccs) cudaFree(c->d_reccs);
   if (c->gvec) cudaFree(c->gvec);
   if (c->gtmp) cudaFree(c->gtmp);
   if (c->h_err) cudaFreeHost(c->h_err);

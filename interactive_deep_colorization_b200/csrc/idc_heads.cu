@@ -603,6 +603,177 @@ cudaError_t launch_global_mlp(Ctx* c, int n, const float* glob, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------------------------------
+// colour suggestions (data/colorize_image.py:322-354): the reference draws 25 000 samples
+// from one pixel's 529-bin pmf and k-means them.  The N -> infinity limit of that procedure is weighted
+// k-means over the 529 gamut points with the pmf as weights; this kernel runs it deterministically in one
+// CTA: greedy farthest-point seeding (first seed = heaviest bin, next = argmax w * d^2), Lloyd iterations in
+// FP64 until the assignment is stable, clusters ordered by mass.  Warp k owns cluster k.
+// ------------------------------------------------------------------------------------------
+constexpr int kReccBins = 529, kReccMaxK = 32;
+
+__device__ __forceinline__ int block_argmax(double v, int idx, double* rv, int* ri) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  if (lane == 0) { rv[warp] = v; ri[warp] = idx; }
+  __syncthreads();
+  if (warp == 0) {
+    v = rv[lane]; idx = ri[lane];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+      if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    if (lane == 0) ri[0] = idx;
+  }
+  __syncthreads();
+  const int r = ri[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(1024) ab_reccs_kernel(const float* __restrict__ pmf, size_t bin_stride,
+                                                        const float* __restrict__ pts, int K, int max_iter,
+                                                        double* __restrict__ out_all) {
+  // CTA v = restart v: its first seed is the bin of weight-rank v (0 = heaviest); out_all[v] = [K][2]
+  // centres, [K] mass, iterations, inertia
+  double* out = out_all + (size_t)blockIdx.x * (3 * K + 2);
+  __shared__ double w[kReccBins], mind[kReccBins];
+  __shared__ double px[kReccBins], py[kReccBins];
+  __shared__ int label[kReccBins];
+  __shared__ double cx[kReccMaxK], cy[kReccMaxK], mass[kReccMaxK], rv[32];
+  __shared__ int ri[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool live = tid < kReccBins;
+
+  // normalised weights (fixed-order tree sum)
+  double v = live ? (double)pmf[(size_t)tid * bin_stride] : 0.0;
+  double s = v;
+#pragma unroll
+  for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) rv[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    s = rv[lane];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) rv[0] = s;
+  }
+  __syncthreads();
+  const double total = rv[0];
+  __syncthreads();
+  if (live) {
+    w[tid] = v / total;
+    px[tid] = (double)pts[2 * tid];
+    py[tid] = (double)pts[2 * tid + 1];
+    label[tid] = -1;
+  }
+  __syncthreads();
+
+  // greedy seeding
+  int rank = 0;
+  if (live && blockIdx.x > 0)
+    for (int j = 0; j < kReccBins; ++j) rank += (w[j] > w[tid]) || (w[j] == w[tid] && j < tid);
+  for (int j = 0; j < K; ++j) {
+    double score = -1.0;
+    if (live) score = j == 0 ? (rank == (int)blockIdx.x ? 2.0 : (blockIdx.x == 0 ? w[tid] : -1.0)) : w[tid] * mind[tid];
+    const int pick = block_argmax(score, live ? tid : 0x7fffffff, rv, ri);
+    if (tid == 0) { cx[j] = px[pick]; cy[j] = py[pick]; }
+    __syncthreads();
+    if (live) {
+      const double dx = px[tid] - cx[j], dy = py[tid] - cy[j];
+      const double d = dx * dx + dy * dy;
+      mind[tid] = j == 0 ? d : fmin(mind[tid], d);
+    }
+  }
+  __syncthreads();
+
+  // Lloyd
+  int iters = 0;
+  for (; iters < max_iter; ++iters) {
+    int changed = 0;
+    if (live) {
+      int best = 0;
+      double bd = INFINITY;
+      for (int k = 0; k < K; ++k) {
+        const double dx = px[tid] - cx[k], dy = py[tid] - cy[k];
+        const double d = dx * dx + dy * dy;
+        if (d < bd) { bd = d; best = k; }
+      }
+      changed = best != label[tid];
+      label[tid] = best;
+    }
+    if (!__syncthreads_or(changed)) break;
+    if (warp < K) {
+      double sw = 0.0, sx = 0.0, sy = 0.0;
+      for (int i = lane; i < kReccBins; i += 32)
+        if (label[i] == warp) { sw += w[i]; sx += w[i] * px[i]; sy += w[i] * py[i]; }
+#pragma unroll
+      for (int off = 16; off; off >>= 1) {
+        sw += __shfl_xor_sync(0xffffffffu, sw, off);
+        sx += __shfl_xor_sync(0xffffffffu, sx, off);
+        sy += __shfl_xor_sync(0xffffffffu, sy, off);
+      }
+      if (lane == 0) {
+        mass[warp] = sw;
+        if (sw > 0.0) { cx[warp] = sx / sw; cy[warp] = sy / sw; }   // an empty cluster keeps its centre
+      }
+    }
+    __syncthreads();
+  }
+
+  // inertia = sum_i w_i * min_k d(i, k) with the final centres (fixed-order tree sum)
+  double e = 0.0;
+  if (live) {
+    double bd = INFINITY;
+    for (int k = 0; k < K; ++k) {
+      const double dx = px[tid] - cx[k], dy = py[tid] - cy[k];
+      bd = fmin(bd, dx * dx + dy * dy);
+    }
+    e = w[tid] * bd;
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+  if (lane == 0) rv[warp] = e;
+  __syncthreads();
+  if (warp == 0) {
+    e = rv[lane];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+    if (lane == 0) out[3 * K + 1] = e;
+  }
+
+  // order by mass, descending, stable
+  if (tid == 0) {
+    int order[kReccMaxK];
+    for (int k = 0; k < K; ++k) order[k] = k;
+    for (int a = 1; a < K; ++a) {
+      const int o = order[a];
+      int b = a - 1;
+      while (b >= 0 && mass[order[b]] < mass[o]) { order[b + 1] = order[b]; --b; }
+      order[b + 1] = o;
+    }
+    for (int k = 0; k < K; ++k) {
+      out[2 * k] = cx[order[k]];
+      out[2 * k + 1] = cy[order[k]];
+      out[2 * K + k] = mass[order[k]];
+    }
+    out[3 * K] = (double)iters;
+  }
+}
+
+cudaError_t launch_ab_reccs(const float* pmf, size_t bin_stride, const float* pts_dev, int K, int max_iter,
+                            int n_init, double* out_dev, cudaStream_t st) {
+  ab_reccs_kernel<<<n_init, 1024, 0, st>>>(pmf, bin_stride, pts_dev, K, max_iter, out_dev);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // test hooks: activation <-> NCHW fp32
 // ------------------------------------------------------------------------------------------
 __global__ void act_to_nchw_kernel(const float* f, const __half* hi, const __half* lo, int N, int H, int W, int C,

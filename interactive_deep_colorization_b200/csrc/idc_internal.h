@@ -161,6 +161,7 @@ struct Ctx {
   int graph_launches = 0;
   bool gadd_active = false;     // a global-hints vector was supplied to this forward
   int last_n = 0;
+  double* d_reccs = nullptr;    // idc_ab_reccs scratch (results of every restart, then the 529x2 gamut points)
   bool dist_resident = false;   // keep the dist of the last forward_host on the device (idc_fetch_dist)
   int dist_valid_n = 0;
   // per-op profiling
@@ -184,6 +185,8 @@ cudaError_t launch_lab2rgb(int n, int h, int w, const float* L, float l_offset, 
                            uint8_t* rgb, cudaStream_t st);
 cudaError_t launch_decode313(Ctx* c, int n, float T, float* out_ab, cudaStream_t st);
 cudaError_t launch_dist313_pixel(Ctx* c, int img, int y, int x, float S, float* out313_dev, cudaStream_t st);
+cudaError_t launch_ab_reccs(const float* pmf, size_t bin_stride, const float* pts_dev, int K, int max_iter,
+                            int n_init, double* out_dev, cudaStream_t st);
 cudaError_t launch_global_stats(int h, int w, const uint8_t* rgb, const float* pts, float* out316, cudaStream_t st);
 cudaError_t launch_rgb2lab(int n, int h, int w, const uint8_t* rgb, double* lab, cudaStream_t st);
 cudaError_t launch_zoom_lab2rgb(const double* ab, int hin, int win, const double* Lfull, int H, int W, uint8_t* rgb,

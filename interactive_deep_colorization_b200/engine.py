@@ -138,6 +138,17 @@ class LhnContext(object):
             _lib.check(self.h, self.lib.idc_fetch_dist(self.h, img, int(y4), int(x4), _np_ptr(out)))
         return out
 
+    def ab_reccs(self, img, y4, x4, K=5, max_iter=100, n_init=8, pts=None):
+        """Colour suggestions at dist[img, :, y4, x4] (reference get_ab_reccs, data/colorize_image.py:322-354)
+        computed on the device: (centres [K,2], mass [K], Lloyd iterations)."""
+        centers, conf, iters = np.empty((K, 2), np.float32), np.empty((K,), np.float32), ctypes.c_int(0)
+        p = None if pts is None else np.ascontiguousarray(pts, np.float32)
+        assert p is None or p.shape == (529, 2)
+        _lib.check(self.h, self.lib.idc_ab_reccs(self.h, int(img), int(y4), int(x4), int(K), int(max_iter), int(n_init),
+                                                 None if p is None else _np_ptr(p), _np_ptr(centers), _np_ptr(conf),
+                                                 ctypes.byref(iters)))
+        return centers, conf, iters.value
+
     # ---- Caffe-spec 313-bin head (IDC_FLAG_CAFFE313) ----------------------------------------
     def caffe313_pred_ab(self, n, T=2.6):
         """Annealed-mean ab [n,2,H,W] (device tensor) from the 313-bin logits of the last forward."""

@@ -71,3 +71,21 @@ def global_stats_gpu(rgb_u8, device=0):
     if rc != _lib.IDC_OK:
         raise _lib.IdcError(rc, "idc_global_stats failed")
     return d_out.cpu().numpy()
+
+
+def ab_reccs_pmf_gpu(pmf, K=5, max_iter=100, n_init=8, pts=None, device=0):
+    """Colour suggestions for one 529-bin pmf (host array): the deterministic weighted-k-means form of the
+    reference's get_ab_reccs (data/colorize_image.py:322-354), see include/idc_b200.h: idc_ab_reccs_pmf.
+    Returns (centres [K,2], mass [K], Lloyd iterations)."""
+    import ctypes
+    p = np.ascontiguousarray(pmf, np.float32)
+    assert p.shape == (529,)
+    q = None if pts is None else np.ascontiguousarray(pts, np.float32)
+    assert q is None or q.shape == (529, 2)
+    centers, conf, iters = np.empty((K, 2), np.float32), np.empty((K,), np.float32), ctypes.c_int(0)
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+    rc = _lib.load().idc_ab_reccs_pmf(device, vp(p), int(K), int(max_iter), int(n_init), None if q is None else vp(q),
+                                      vp(centers), vp(conf), ctypes.byref(iters))
+    if rc != _lib.IDC_OK:
+        raise _lib.IdcError(rc, "idc_ab_reccs_pmf failed")
+    return centers, conf, iters.value

@@ -68,6 +68,6 @@ def test_reccs_are_sorted_by_mass():
     cd.dist_ab = CI._LazyUpsampledDist(np.tile(pmf[:, None, None], (1, 4, 4)))
     cd.dist_ab_set = True
     np.random.seed(0)
-    centers, conf = cd.get_ab_reccs(5, 5, K=3, N=5000, return_conf=True)
+    centers, conf = cd.get_ab_reccs(5, 5, K=3, N=5000, return_conf=True, method='sampled')
     assert np.allclose(centers[0], cd.pts_in_hull[10]) and np.allclose(centers[2], cd.pts_in_hull[500])
     assert conf[0] > conf[1] > conf[2] and abs(conf.sum() - 1) < 1e-9
