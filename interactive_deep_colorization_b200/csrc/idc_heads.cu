@@ -677,11 +677,11 @@ __global__ void __launch_bounds__(1024) ab_reccs_kernel(const float* __restrict_
 
   // greedy seeding
   int rank = 0;
-  if (live && blockIdx.x > 0)
+  if (live)
     for (int j = 0; j < kReccBins; ++j) rank += (w[j] > w[tid]) || (w[j] == w[tid] && j < tid);
   for (int j = 0; j < K; ++j) {
     double score = -1.0;
-    if (live) score = j == 0 ? (rank == (int)blockIdx.x ? 2.0 : (blockIdx.x == 0 ? w[tid] : -1.0)) : w[tid] * mind[tid];
+    if (live) score = j == 0 ? (rank == (int)blockIdx.x ? 2.0 : -1.0) : w[tid] * mind[tid];
     const int pick = block_argmax(score, live ? tid : 0x7fffffff, rv, ri);
     if (tid == 0) { cx[j] = px[pick]; cy[j] = py[pick]; }
     __syncthreads();
