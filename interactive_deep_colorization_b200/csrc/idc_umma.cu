@@ -138,6 +138,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
       : "memory");
 }
 
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -247,6 +252,19 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
+}
+
+// 32 FP32 values -> 16 packed f16x2 words of the hi plane (+ 16 of the lo plane = value - hi, when SPLIT)
+template <bool SPLIT>
+__device__ __forceinline__ void split_pack(const float (&f)[32], uint32_t (&hw)[16], uint32_t (&lw)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    hw[j] = pack_f16x2_sat(f[2 * j], f[2 * j + 1]);
+    if (SPLIT) {
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+      lw[j] = pack_f16x2_sat(f[2 * j] - hf.x, f[2 * j + 1] - hf.y);
+    }
+  }
 }
 
 __device__ __forceinline__ void split_h(float v, __half& hi, __half& lo) {
@@ -611,37 +629,17 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           }
         }
       }
-      if (!(p.dbg & 2)) {
-      // ---- epilogue on the register accumulators, 32 output channels at a time ----
-      const int ty0 = (r2 / p.tiles_x) * (p.hbox * MT) + (MT == 2 ? half * p.hbox : 0);
-      const int tx0 = (r2 % p.tiles_x) * p.wbox;
-      size_t opix = 0;
-      if (valid) {
-        if (p.out_f32) opix = ((size_t)(img * p.Hl + y) * p.Wl + x) * p.out_ld + n0 + c_base;
-        else opix = ((size_t)(img * p.Hout + y * p.os + (cls >> 1)) * p.Wout + x * p.os + (cls & 1)) * p.Cout + n0 + c_base;
-      }
-      // warp-transposed stores: store instruction i of a slab covers rows i*8 + lane/4 of this warp's 32 rows
-      size_t tbase[4];
-      bool tvalid[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rr = quarter * 32 + i * 8 + (lane >> 2);
-        const int yy = ty0 + (rr >> p.wshift), xx = tx0 + (rr & (p.wbox - 1));
-        tvalid[i] = yy < p.Hl && xx < p.Wl && img < p.n_img;
-        tbase[i] = ((size_t)(img * p.Hout + yy * p.os + (cls >> 1)) * p.Wout + xx * p.os + (cls & 1)) * p.Cout + n0 + c_base +
-                   (lane & 3) * 8;
-      }
+      // ---- epilogue on the register accumulators, 32 output channels at a time.  The output kind is uniform for
+      //      the launch, so the branch sits outside the slab loops; the per-channel vectors are read with
+      //      ld.shared (warp-uniform 16-byte reads), never through generic addressing. ----
+      const uint32_t sv = smem_u32(s_bias) + (uint32_t)c_base * 4u;   // bias | +BN*4: scale | +2*BN*4: shift
       const float neg_slope = p.act == ACT_RELU ? 0.f : (p.act == ACT_LEAKY02 ? 0.2f : 1.f);
-      float h0 = 0.f, h1 = 0.f;
+      auto slab = [&](const int ch, float (&f)[32]) {
 #pragma unroll
-      for (int ch = 0; ch < CH; ch += 32) {
-        if (S > 1 && ((c_base + ch) >> 5) % S != ks) continue;   // another CTA of the split finishes this piece
-        float f[32];
-#pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {      // warp-uniform float4 reads of the staged per-channel vectors
-          const float4 vb = *reinterpret_cast<const float4*>(s_bias + c_base + ch + j4);
-          const float4 vs = *reinterpret_cast<const float4*>(s_scale + c_base + ch + j4);
-          const float4 vt = *reinterpret_cast<const float4*>(s_shift + c_base + ch + j4);
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const float4 vb = ld_shared_f4(sv + (uint32_t)(ch + j4) * 4u);
+          const float4 vs = ld_shared_f4(sv + (uint32_t)(BN + ch + j4) * 4u);
+          const float4 vt = ld_shared_f4(sv + (uint32_t)(2 * BN + ch + j4) * 4u);
           const float b4[4] = {vb.x, vb.y, vb.z, vb.w}, s4[4] = {vs.x, vs.y, vs.z, vs.w}, t4[4] = {vt.x, vt.y, vt.z, vt.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -651,73 +649,24 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
             f[j4 + j] = fmaf(a, s4[j], t4[j]);
           }
         }
-        if (p.wout) {
+      };
+      if (p.wout) {
+        // fused model_out: conv1x1(128->2) + tanh, x110 (model.py:108-109,175)
+        const uint32_t sh = smem_u32(s_head) + (uint32_t)c_base * 4u;
+        float h0 = 0.f, h1 = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < CH; ch += 32) {
+          float f[32];
+          slab(ch, f);
 #pragma unroll
           for (int j4 = 0; j4 < 32; j4 += 4) {
-            const float4 w0 = *reinterpret_cast<const float4*>(s_head + c_base + ch + j4);
-            const float4 w1 = *reinterpret_cast<const float4*>(s_head + 128 + c_base + ch + j4);
+            const float4 w0 = ld_shared_f4(sh + (uint32_t)(ch + j4) * 4u);
+            const float4 w1 = ld_shared_f4(sh + (uint32_t)(128 + ch + j4) * 4u);
             h0 = fmaf(f[j4], w0.x, fmaf(f[j4 + 1], w0.y, fmaf(f[j4 + 2], w0.z, fmaf(f[j4 + 3], w0.w, h0))));
             h1 = fmaf(f[j4], w1.x, fmaf(f[j4 + 1], w1.y, fmaf(f[j4 + 2], w1.z, fmaf(f[j4 + 3], w1.w, h1))));
           }
-        } else if (p.out_f32) {
-          if (valid && !(p.dbg & 1)) {
-            float4* o = reinterpret_cast<float4*>(p.out_f32 + opix + ch);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-          }
-        } else if (!(p.dbg & 1)) {
-          // hi/lo split, packed two channels per 32-bit word
-          uint32_t hw[16], lw[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            hw[j] = pack_f16x2_sat(f[2 * j], f[2 * j + 1]);
-            if (SPLIT) {
-              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
-              lw[j] = pack_f16x2_sat(f[2 * j] - hf.x, f[2 * j + 1] - hf.y);
-            }
-          }
-          if (p.store_mode == 0) {
-            // direct: every lane stores its own pixel row (one L1 transaction per lane per instruction)
-            if (valid) {
-              uint4* oh = reinterpret_cast<uint4*>(p.out_hi + opix + ch);
-              uint4* ol = SPLIT ? reinterpret_cast<uint4*>(p.out_lo + opix + ch) : nullptr;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                oh[q] = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
-                if (SPLIT) ol[q] = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
-              }
-            }
-          } else {
-            // warp-transposed: the warp's 32 rows x 64 bytes go through a private 2 KB smem tile (XOR-swizzled,
-            // conflict-free both ways) so that each store instruction writes 8 pixel rows x 64 contiguous
-            // bytes instead of 32 rows x 16 bytes -- 4x fewer L1 transactions, no completion wait.
-            const uint32_t wbuf = smem_u32(s_out) + (warp - 4) * 2048;
-#pragma unroll
-            for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane) {
-              const uint32_t* src = plane == 0 ? hw : lw;
-#pragma unroll
-              for (int c = 0; c < 4; ++c)
-                st_shared_v4(wbuf + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4),
-                             make_uint4(src[4 * c], src[4 * c + 1], src[4 * c + 2], src[4 * c + 3]));
-              __syncwarp();
-              __half* gbase = plane == 0 ? p.out_hi : p.out_lo;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int rl = i * 8 + (lane >> 2), c = lane & 3;          // row of this warp's 32, 16-byte chunk
-                uint4 v;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                             : "r"(wbuf + rl * 64 + ((c ^ ((rl >> 1) & 3)) << 4)));
-                if (tvalid[i]) *reinterpret_cast<uint4*>(gbase + tbase[i] + ch) = v;
-              }
-              __syncwarp();
-            }
-          }
         }
-      }
-      if (p.wout) {
-        // model_out: conv1x1(128->2) + tanh, x110 (model.py:108-109,175); the two column halves of a
-        // pixel live in two warps -> combine through smem
+        // the two column halves of a pixel live in two warps when MT == 1 -> combine through smem
         if (MT == 1) {
           if (half == 1) { s_red[row * 2] = h0; s_red[row * 2 + 1] = h1; }
           asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -730,7 +679,91 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           p.out_ab[o] = tanhf(h0 + s_head[256]) * 110.0f * p.out_mult;
           p.out_ab[o + HW] = tanhf(h1 + s_head[257]) * 110.0f * p.out_mult;
         }
-      }
+      } else if (p.out_f32) {
+        float* o32 = p.out_f32 + ((size_t)(img * p.Hl + y) * p.Wl + x) * p.out_ld + n0 + c_base;
+#pragma unroll
+        for (int ch = 0; ch < CH; ch += 32) {
+          if (S > 1 && ((c_base + ch) >> 5) % S != ks) continue;   // another CTA of the split finishes this piece
+          float f[32];
+          slab(ch, f);
+          if (valid) {
+            float4* o = reinterpret_cast<float4*>(o32 + ch);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+          }
+        }
+      } else if (p.store_mode == 0) {
+        // direct: every lane stores its own pixel row (one L1 transaction per lane per instruction)
+        const size_t opix =
+            ((size_t)(img * p.Hout + y * p.os + (cls >> 1)) * p.Wout + x * p.os + (cls & 1)) * p.Cout + n0 + c_base;
+#pragma unroll
+        for (int ch = 0; ch < CH; ch += 32) {
+          if (S > 1 && ((c_base + ch) >> 5) % S != ks) continue;
+          float f[32];
+          slab(ch, f);
+          uint32_t hw[16], lw[16];
+          split_pack<SPLIT>(f, hw, lw);
+          if (valid) {
+            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + opix + ch);
+            uint4* ol = SPLIT ? reinterpret_cast<uint4*>(p.out_lo + opix + ch) : nullptr;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              oh[q] = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+              if (SPLIT) ol[q] = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+            }
+          }
+        }
+      } else {
+        // warp-transposed (default): the warp's 32 rows x 64 bytes go through a private 2 KB smem tile
+        // (XOR-swizzled, conflict-free both ways) so that each store instruction writes 8 pixel rows x 64
+        // contiguous bytes instead of 32 rows x 16 bytes -- 4x fewer L1 transactions.  Store instruction i of a
+        // slab covers rows i*8 + lane/4 of this warp's 32 rows; rows outside the image get a null pointer.
+        const int ty0 = (r2 / p.tiles_x) * (p.hbox * MT) + (MT == 2 ? half * p.hbox : 0);
+        const int tx0 = (r2 % p.tiles_x) * p.wbox;
+        __half* ph[4];
+        const ptrdiff_t lo_delta = SPLIT ? p.out_lo - p.out_hi : 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = quarter * 32 + i * 8 + (lane >> 2);
+          const int yy = ty0 + (rr >> p.wshift), xx = tx0 + (rr & (p.wbox - 1));
+          const bool ok = yy < p.Hl && xx < p.Wl && img < p.n_img;
+          ph[i] = ok ? p.out_hi + ((size_t)(img * p.Hout + yy * p.os + (cls >> 1)) * p.Wout + xx * p.os + (cls & 1)) * p.Cout +
+                           n0 + c_base + (lane & 3) * 8
+                     : nullptr;
+        }
+        const uint32_t wbuf = smem_u32(s_out) + (warp - 4) * 2048;
+        const uint32_t wst = wbuf + lane * 64, wsw = (lane >> 1) & 3;
+        uint32_t wld[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rl = i * 8 + (lane >> 2), c = lane & 3;          // row of this warp's 32, 16-byte chunk
+          wld[i] = wbuf + rl * 64 + ((c ^ ((rl >> 1) & 3)) << 4);
+        }
+#pragma unroll
+        for (int ch = 0; ch < CH; ch += 32) {
+          if (S > 1 && ((c_base + ch) >> 5) % S != ks) continue;
+          float f[32];
+          slab(ch, f);
+          uint32_t hw[16], lw[16];
+          split_pack<SPLIT>(f, hw, lw);
+#pragma unroll
+          for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane) {
+            const uint32_t* src = plane == 0 ? hw : lw;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              st_shared_v4(wst + ((c ^ wsw) << 4), make_uint4(src[4 * c], src[4 * c + 1], src[4 * c + 2], src[4 * c + 3]));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 v;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                           : "r"(wld[i]));
+              if (ph[i]) *reinterpret_cast<uint4*>(ph[i] + (plane ? lo_delta : 0) + ch) = v;
+            }
+            __syncwarp();
+          }
+        }
       }
       if (IDC_CTA_COUNTERS && p.dbgbuf) t_epi += clock64() - tE;
       if (S > 1) {
