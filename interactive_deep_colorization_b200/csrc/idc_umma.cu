@@ -643,9 +643,10 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           const float b4[4] = {vb.x, vb.y, vb.z, vb.w}, s4[4] = {vs.x, vs.y, vs.z, vs.w}, t4[4] = {vt.x, vt.y, vt.z, vt.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            // one branch-free form for none / ReLU / LeakyReLU(0.2): max(t,0) + slope*min(t,0), slope = 1 / 0 / 0.2
+            // one branch-free form for none / ReLU / LeakyReLU(0.2): max(t, slope*t) with slope = 1 / 0 / 0.2
+            // (slope <= 1, so slope*t >= t exactly when t <= 0; one rounding, same value as slope*t alone)
             const float t = acc[ch + j4 + j] + b4[j];
-            const float a = fmaf(neg_slope, fminf(t, 0.f), fmaxf(t, 0.f));
+            const float a = fmaxf(t, neg_slope * t);
             f[j4 + j] = fmaf(a, s4[j], t4[j]);
           }
         }
