@@ -307,9 +307,9 @@ def run_ours(args):
                        "l2_policy": "per-step working set (~%.1f GB of activations) >> 126 MB L2; inputs are not re-used from L2"
                                     % (N * 0.15)},
             "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(N * 4 * X * X * 4),
-                    "d2h_bytes_per_step": int(N * 2 * X * X * 4)},
-            "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "latency": lat,
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(world * N * 4 * X * X * 4),
+                    "d2h_bytes_per_step": int(world * N * 2 * X * X * 4)},      # whole job, all ranks
+            "gpu_launches": world * launches_per_step * args.steps, "clocks": clocks, "latency": lat,
             "per_op_ms": {n: round(ms, 4) for n, ms, _ in prof}}
     print(json.dumps(line))
     if world > 1:
