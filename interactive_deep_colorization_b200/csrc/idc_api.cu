@@ -477,8 +477,17 @@ int plan_engines(Ctx* c) {
   return IDC_OK;
 }
 
+// idc_forward_host's copy/compute overlap: the batch is cut into image chunks; conv1_1 of chunk k waits for the
+// H2D of chunk k only (issued on Ctx::s_in), and the last op (c10_2 + fused model_out) runs per chunk so that the
+// D2H of ab chunk k (on Ctx::s_out) overlaps the compute of chunk k+1.  Everything in between runs on the whole batch.
+struct HostPipe {
+  int nchunks = 0;
+  int start[5] = {};          // image ranges [start[k], start[k+1])
+  float* ab_dst = nullptr;    // pinned host destination of out_ab (caller's buffer or the staging block)
+};
+
 int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mask, float maskcent, const float* glob,
-                float* out_ab, float* out_dist, uint8_t* out_rgb, cudaStream_t st) {
+                float* out_ab, float* out_dist, uint8_t* out_rgb, cudaStream_t st, const HostPipe* hp = nullptr) {
   c->launch_count = 0;
   c->gadd_active = false;
   std::vector<cudaEvent_t>* ev = nullptr;
@@ -492,15 +501,36 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
   };
   if (c->profiling) { c->prof_runs.emplace_back(); ev = &c->prof_runs.back(); }
   mark();
+  if (hp) CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_in[0], 0));     // covers the glob vector too
   if (glob && c->glob) {
     CUDA_TRY(c, launch_global_mlp(c, n, glob, st));
     c->gadd_active = true;
   }
-  CUDA_TRY(c, launch_conv1_1(c, n, L, ab, mask, maskcent, st));
+  const size_t HW = (size_t)c->H * c->W;
+  if (hp) {
+    for (int k = 0; k < hp->nchunks; ++k) {
+      CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_in[k], 0));
+      CUDA_TRY(c, launch_conv1_1(c, hp->start[k + 1] - hp->start[k], L, ab, mask, maskcent, st, hp->start[k]));
+    }
+  } else {
+    CUDA_TRY(c, launch_conv1_1(c, n, L, ab, mask, maskcent, st));
+  }
   mark();
   for (auto& op : c->ops) {
-    if (c->simt) CUDA_TRY(c, simt_run_op(c, op, n, st));
-    else CUDA_TRY(c, umma_run_op(c, op, n, op.fuse_out_head ? out_ab : nullptr, 1.0f, st));
+    if (c->simt) {
+      CUDA_TRY(c, simt_run_op(c, op, n, st));
+    } else if (hp && op.fuse_out_head) {
+      for (int k = 0; k < hp->nchunks; ++k) {
+        const int i0 = hp->start[k], nk = hp->start[k + 1] - i0;
+        CUDA_TRY(c, umma_run_op(c, op, nk, out_ab, 1.0f, st, i0));
+        CUDA_TRY(c, cudaEventRecord(c->ev_out[k], st));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->s_out, c->ev_out[k], 0));
+        CUDA_TRY(c, cudaMemcpyAsync(hp->ab_dst + (size_t)i0 * 2 * HW, out_ab + (size_t)i0 * 2 * HW,
+                                    (size_t)nk * 2 * HW * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
+      }
+    } else {
+      CUDA_TRY(c, umma_run_op(c, op, n, op.fuse_out_head ? out_ab : nullptr, 1.0f, st));
+    }
     mark();
   }
   const bool fused = !c->simt && !(c->flags & IDC_FLAG_KEEP_CONV10);
@@ -676,12 +706,45 @@ int idc_forward_host(idc_ctx* c, int n, int h, int w, const float* L, const floa
     }
     return cudaMemcpyAsync(d, s, count * sizeof(float), cudaMemcpyHostToDevice, st);
   };
-  CUDA_TRY(c, h2d(dL, L, n * HW, 0));
-  CUDA_TRY(c, h2d(dab, ab, n * 2 * HW, (size_t)c->max_n * HW));
-  CUDA_TRY(c, h2d(dmask, mask, n * HW, (size_t)c->max_n * 3 * HW));
-  if (glob) CUDA_TRY(c, h2d(dglob, glob, (size_t)n * 316, (size_t)c->max_n * 4 * HW));
-
   const bool use_graph = !(c->flags & IDC_FLAG_NO_GRAPH) && n <= 4;
+  // large batches: chunked copy/compute overlap (see HostPipe); IDC_HOST_PIPE=0 turns it off for A/B runs
+  static const bool pipe_env = !(getenv("IDC_HOST_PIPE") && atoi(getenv("IDC_HOST_PIPE")) == 0);
+  const bool fused_head = !c->simt && !(c->flags & IDC_FLAG_KEEP_CONV10);
+  HostPipe hp;
+  bool last_splits = false;
+  for (auto& op : c->ops) if (op.fuse_out_head) last_splits = umma_op_uses_split_k(op);
+  if (pipe_env && !use_graph && n >= 8 && fused_head && !last_splits && !c->profiling) {
+    hp.nchunks = n >= 32 ? 4 : 2;
+    for (int k = 0; k <= hp.nchunks; ++k) hp.start[k] = (int)((long long)n * k / hp.nchunks);
+    hp.ab_dst = is_pinned(out_ab) ? out_ab : c->h_out;
+    if (!c->s_in) {
+      CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+      CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+      for (int k = 0; k < 4; ++k) {
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_out[k], cudaEventDisableTiming));
+      }
+    }
+  }
+  if (hp.nchunks) {
+    cudaStream_t compute = st;
+    st = c->s_in;                                   // the h2d lambda copies on `st`
+    if (glob) CUDA_TRY(c, h2d(dglob, glob, (size_t)n * 316, (size_t)c->max_n * 4 * HW));
+    for (int k = 0; k < hp.nchunks; ++k) {
+      const size_t i0 = hp.start[k], nk = hp.start[k + 1] - hp.start[k];
+      CUDA_TRY(c, h2d(dL + i0 * HW, L + i0 * HW, nk * HW, i0 * HW));
+      CUDA_TRY(c, h2d(dab + i0 * 2 * HW, ab + i0 * 2 * HW, nk * 2 * HW, (size_t)c->max_n * HW + i0 * 2 * HW));
+      CUDA_TRY(c, h2d(dmask + i0 * HW, mask + i0 * HW, nk * HW, (size_t)c->max_n * 3 * HW + i0 * HW));
+      CUDA_TRY(c, cudaEventRecord(c->ev_in[k], c->s_in));
+    }
+    st = compute;
+  } else {
+    CUDA_TRY(c, h2d(dL, L, n * HW, 0));
+    CUDA_TRY(c, h2d(dab, ab, n * 2 * HW, (size_t)c->max_n * HW));
+    CUDA_TRY(c, h2d(dmask, mask, n * HW, (size_t)c->max_n * 3 * HW));
+    if (glob) CUDA_TRY(c, h2d(dglob, glob, (size_t)n * 316, (size_t)c->max_n * 4 * HW));
+  }
+
   const bool copy_dist = out_dist != nullptr;
   const bool want_dist = copy_dist || (c->dist_resident && c->dist);
   const bool want_rgb = out_rgb != nullptr, want_glob = glob != nullptr;
@@ -710,17 +773,18 @@ int idc_forward_host(idc_ctx* c, int n, int h, int w, const float* L, const floa
     c->launch_count = c->graph_launches;
   } else {
     rc = run_forward(c, n, dL, dab, dmask, maskcent, want_glob ? dglob : nullptr, dout, want_dist ? ddist : nullptr,
-                     want_rgb ? c->d_rgb : nullptr, st);
+                     want_rgb ? c->d_rgb : nullptr, st, hp.nchunks ? &hp : nullptr);
     if (rc != IDC_OK) return rc;
   }
   auto d2h = [&](void* dst, const void* d, size_t bytes, void* stage) -> cudaError_t {
     if (is_pinned(dst)) return cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, st);
     return cudaMemcpyAsync(stage, d, bytes, cudaMemcpyDeviceToHost, st);
   };
-  CUDA_TRY(c, d2h(out_ab, dout, n * 2 * HW * sizeof(float), c->h_out));
+  if (!hp.nchunks) CUDA_TRY(c, d2h(out_ab, dout, n * 2 * HW * sizeof(float), c->h_out));
   if (copy_dist) CUDA_TRY(c, d2h(out_dist, ddist, n * 529 * HW4 * sizeof(float), c->h_out + (size_t)c->max_n * 2 * HW));
   if (want_rgb) CUDA_TRY(c, d2h(out_rgb, c->d_rgb, n * HW * 3, c->h_rgb));
   CUDA_TRY(c, cudaStreamSynchronize(st));
+  if (hp.nchunks) CUDA_TRY(c, cudaStreamSynchronize(c->s_out));
   if (!is_pinned(out_ab)) memcpy(out_ab, c->h_out, n * 2 * HW * sizeof(float));
   if (copy_dist && !is_pinned(out_dist)) memcpy(out_dist, c->h_out + (size_t)c->max_n * 2 * HW, n * 529 * HW4 * sizeof(float));
   c->dist_valid_n = want_dist ? n : 0;
@@ -1004,6 +1068,10 @@ int idc_destroy(idc_ctx* c) {
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_rgb) cudaFreeHost(c->h_rgb);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->s_in) {
+    cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);
+    for (int k = 0; k < 4; ++k) { cudaEventDestroy(c->ev_in[k]); cudaEventDestroy(c->ev_out[k]); }
+  }
   delete c;
   return IDC_OK;
 }

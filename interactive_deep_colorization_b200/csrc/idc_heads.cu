@@ -111,16 +111,17 @@ __global__ void __launch_bounds__(128) conv1_1_kernel(const __grid_constant__ Co
 }
 
 cudaError_t launch_conv1_1(Ctx* c, int n, const float* L, const float* ab, const float* mask, float maskcent,
-                           cudaStream_t st) {
+                           cudaStream_t st, int img0) {
   const ActBuf& o = c->bufs[c->buf_index.at("a1_1")];
-  const size_t npix = (size_t)n * o.H * o.W;
+  const size_t HW = (size_t)o.H * o.W, npix = (size_t)n * HW, ooff = (size_t)img0 * HW * o.C;
   const int grid = (int)((npix + 127) / 128);
+  L += img0 * HW; ab += img0 * 2 * HW; mask += img0 * HW;
   if (c->simt)
     conv1_1_kernel<false><<<grid, 128, 0, st>>>(c->h_w11, L, ab, mask, maskcent, n, o.H, o.W,
-                                                static_cast<float*>(o.p0), nullptr, nullptr);
+                                                static_cast<float*>(o.p0) + ooff, nullptr, nullptr);
   else
     conv1_1_kernel<true><<<grid, 128, 0, st>>>(c->h_w11, L, ab, mask, maskcent, n, o.H, o.W, nullptr,
-                                               static_cast<__half*>(o.p0), static_cast<__half*>(o.p1));
+                                               static_cast<__half*>(o.p0) + ooff, static_cast<__half*>(o.p1) + ooff);
   c->launch_count++;
   return cudaGetLastError();
 }

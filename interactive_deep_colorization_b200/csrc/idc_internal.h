@@ -153,6 +153,10 @@ struct Ctx {
   float* h_out = nullptr; float* d_out = nullptr;  size_t out_floats = 0;
   uint8_t* h_rgb = nullptr; uint8_t* d_rgb = nullptr;
   cudaStream_t own_stream = nullptr;
+  // idc_forward_host pipeline (large batches): H2D of image chunk k+1 overlaps conv1_1 of chunk k, D2H of ab
+  // chunk k overlaps the last op of chunk k+1
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[4] = {}, ev_out[4] = {};
   // CUDA graph cache for the batch-1 latency path
   cudaGraphExec_t graph_exec = nullptr;
   const void* graph_ptrs[8] = {nullptr};
@@ -175,10 +179,11 @@ struct Ctx {
 cudaError_t simt_run_op(Ctx* c, ConvOp& op, int n, cudaStream_t st);
 int umma_plan_op(Ctx* c, ConvOp& op);              // builds tensor maps; returns IDC_* code
 void umma_free_op(ConvOp& op);
-cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float out_mult, cudaStream_t st);
+cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float out_mult, cudaStream_t st, int img0 = 0);
+bool umma_op_uses_split_k(const ConvOp& op);
 
 cudaError_t launch_conv1_1(Ctx* c, int n, const float* L, const float* ab, const float* mask,
-                           float maskcent, cudaStream_t st);
+                           float maskcent, cudaStream_t st, int img0 = 0);   // L/ab/mask: full arrays; images img0..img0+n
 cudaError_t launch_out_head(Ctx* c, int n, float* out_ab, cudaStream_t st);   // SIMT / KEEP_CONV10 path
 cudaError_t launch_softmax529(Ctx* c, int n, float* out_dist, cudaStream_t st);
 cudaError_t launch_lab2rgb(int n, int h, int w, const float* L, float l_offset, const float* ab,

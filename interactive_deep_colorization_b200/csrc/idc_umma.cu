@@ -68,7 +68,8 @@ struct UmmaParams {
   float out_mult;
   int* err;
   long long* dbgbuf;   // experiments only: per-CTA cycle counters [grid][8]
-  int dbg;             // experiments only (IDC_DEBUG_SKIP): 1 = skip activation stores, 2 = skip the whole epilogue
+  int img0;            // first image of this launch (n_img = img0 + images of the launch): idc_forward_host
+                       // runs the last op in image chunks so that the D2H of a chunk overlaps the next one
 };
 
 // ------------------------------------------------------------------------------------------
@@ -380,8 +381,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         const int cls = r % p.ncls;
         r /= p.ncls;
         if (PAIR) r = 2 * r + (int)cta_rank;
-        const int img = r / tiles_per_img;
-        r -= img * tiles_per_img;
+        const int img_rel = r / tiles_per_img;
+        r -= img_rel * tiles_per_img;
+        const int img = p.img0 + img_rel;
         const int y0 = (r / p.tiles_x) * (p.hbox * MT), x0 = (r % p.tiles_x) * p.wbox;
         const int brow = cls * p.cout_pad + nt * BN + (int)cta_rank * (BN / CG);
         const int4* kb = p.kblk + cls * p.nkb;                  // read-only table in global memory (L1-resident)
@@ -516,8 +518,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       const int cls = r % p.ncls;
       r /= p.ncls;
       if (PAIR) r = 2 * r + (int)cta_rank;
-      const int img = r / tiles_per_img;
-      r -= img * tiles_per_img;
+      const int img_rel = r / tiles_per_img;
+      r -= img_rel * tiles_per_img;
+      const int img = p.img0 + img_rel;
       const int r2 = r;
       const int y = (r / p.tiles_x) * (p.hbox * MT) + (MT == 2 ? half * p.hbox : 0) + (row >> p.wshift);
       const int x = (r % p.tiles_x) * p.wbox + (row & (p.wbox - 1));
@@ -1007,9 +1010,8 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   q.store_mode = 1;
   if (const char* e = getenv("IDC_DIRECT_STORES")) { if (atoi(e)) q.store_mode = 0; }
   q.err = c->d_err;
-  q.dbg = 0;
+  q.img0 = 0;
   q.dbgbuf = nullptr;
-  if (const char* e = getenv("IDC_DEBUG_SKIP")) q.dbg = atoi(e);
   // split-K for launches that cannot fill the machine even at the ctx's max batch (interactive path)
   {
     const long T = (long)op.ncls * c->max_n * q.tiles_y * q.tiles_x * q.n_tiles_n;
@@ -1042,11 +1044,18 @@ void umma_free_op(ConvOp& op) {
   op.umma_plan = nullptr;
 }
 
-cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float out_mult, cudaStream_t st) {
+bool umma_op_uses_split_k(const ConvOp& op) {
+  const UmmaPlan* pl = static_cast<const UmmaPlan*>(op.umma_plan);
+  return pl && pl->split_k > 1;
+}
+
+cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float out_mult, cudaStream_t st, int img0) {
   UmmaPlan* pl = static_cast<UmmaPlan*>(op.umma_plan);
   if (!pl) return cudaErrorInvalidValue;
   UmmaParams prm = pl->prm;
-  prm.n_img = n;
+  prm.img0 = img0;
+  prm.n_img = img0 + n;
+  if (img0 && pl->split_k > 1) return cudaErrorInvalidValue;   // image chunks are a large-batch feature
   const int m_tiles = n * prm.tiles_y * prm.tiles_x;
   prm.total_tiles = op.ncls * (pl->cg == 2 ? (m_tiles + 1) / 2 : m_tiles) * prm.n_tiles_n;
   prm.gadd = (op.epi.gadd && c->gadd_active) ? c->gvec : nullptr;

@@ -317,3 +317,23 @@ def test_odd_geometries(synth_sd, H, W, n):
         assert util.maxabs(r["ab"], ref[0]) <= TOL_AB, (H, W, forced_pairs)
         assert util.maxabs(r["dist"], ref[1]) < 1e-5
         ctx.close()
+
+
+@pytest.mark.parametrize("n,pinned", [(20, False), (40, True), (9, True)])
+def test_host_pipeline_matches_device_path(synth_sd, n, pinned):
+    """idc_forward_host cuts batches >= 8 into image chunks (H2D / conv1_1 and last op / D2H overlap); the result
+    must be bit-identical to the single-shot device-pointer path, for pinned and pageable caller memory."""
+    L, ab, m = synth.synthetic_batch(n, 64, seed=3, max_hints=4)
+    ctx = util.make_ctx(synth_sd, 64, 64, max_n=n)
+    ref = ctx.forward_device(util.dev(L), util.dev(ab), util.dev(m), 0.5, want_rgb=True)
+    ref_ab, ref_rgb = ref["ab"].cpu().numpy(), ref["rgb"].cpu().numpy()
+    if pinned:
+        L, ab, m = (torch.from_numpy(a).pin_memory().numpy() for a in (L, ab, m))
+        out_ab = torch.empty((n, 2, 64, 64), dtype=torch.float32).pin_memory().numpy()
+    else:
+        out_ab = None
+    for _ in range(2):                                  # second call re-uses streams / events
+        r = ctx.forward_host(L, ab, m, 0.5, want_rgb=True, out_ab=out_ab)
+        assert np.array_equal(r["ab"], ref_ab) and np.array_equal(r["rgb"], ref_rgb)
+    assert ctx.last_launch_count() > 27                 # conv1_1 and the last op ran once per chunk
+    ctx.close()
