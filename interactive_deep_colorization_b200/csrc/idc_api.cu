@@ -481,8 +481,9 @@ int plan_engines(Ctx* c) {
 // H2D of chunk k only (issued on Ctx::s_in), and the last op (c10_2 + fused model_out) runs per chunk so that the
 // D2H of ab chunk k (on Ctx::s_out) overlaps the compute of chunk k+1.  Everything in between runs on the whole batch.
 struct HostPipe {
+  static constexpr int kMaxChunks = 8;   // == the size of Ctx::ev_in / ev_out
   int nchunks = 0;
-  int start[5] = {};          // image ranges [start[k], start[k+1])
+  int start[kMaxChunks + 1] = {};        // image ranges [start[k], start[k+1])
   float* ab_dst = nullptr;    // pinned host destination of out_ab (caller's buffer or the staging block)
 };
 
@@ -714,13 +715,13 @@ int idc_forward_host(idc_ctx* c, int n, int h, int w, const float* L, const floa
   bool last_splits = false;
   for (auto& op : c->ops) if (op.fuse_out_head) last_splits = umma_op_uses_split_k(op);
   if (pipe_env && !use_graph && n >= 8 && fused_head && !last_splits && !c->profiling) {
-    hp.nchunks = n >= 32 ? 4 : 2;
+    hp.nchunks = n >= 64 ? 8 : (n >= 32 ? 4 : 2);
     for (int k = 0; k <= hp.nchunks; ++k) hp.start[k] = (int)((long long)n * k / hp.nchunks);
     hp.ab_dst = is_pinned(out_ab) ? out_ab : c->h_out;
     if (!c->s_in) {
       CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
       CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < HostPipe::kMaxChunks; ++k) {
         CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
         CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_out[k], cudaEventDisableTiming));
       }
@@ -1070,7 +1071,7 @@ int idc_destroy(idc_ctx* c) {
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->s_in) {
     cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);
-    for (int k = 0; k < 4; ++k) { cudaEventDestroy(c->ev_in[k]); cudaEventDestroy(c->ev_out[k]); }
+    for (int k = 0; k < HostPipe::kMaxChunks; ++k) { cudaEventDestroy(c->ev_in[k]); cudaEventDestroy(c->ev_out[k]); }
   }
   delete c;
   return IDC_OK;

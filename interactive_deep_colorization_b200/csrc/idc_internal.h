@@ -156,7 +156,7 @@ struct Ctx {
   // idc_forward_host pipeline (large batches): H2D of image chunk k+1 overlaps conv1_1 of chunk k, D2H of ab
   // chunk k overlaps the last op of chunk k+1
   cudaStream_t s_in = nullptr, s_out = nullptr;
-  cudaEvent_t ev_in[4] = {}, ev_out[4] = {};
+  cudaEvent_t ev_in[8] = {}, ev_out[8] = {};
   // CUDA graph cache for the batch-1 latency path
   cudaGraphExec_t graph_exec = nullptr;
   const void* graph_ptrs[8] = {nullptr};

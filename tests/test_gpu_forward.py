@@ -319,7 +319,7 @@ def test_odd_geometries(synth_sd, H, W, n):
         ctx.close()
 
 
-@pytest.mark.parametrize("n,pinned", [(20, False), (40, True), (9, True)])
+@pytest.mark.parametrize("n,pinned", [(20, False), (40, True), (9, True), (67, True)])
 def test_host_pipeline_matches_device_path(synth_sd, n, pinned):
     """idc_forward_host cuts batches >= 8 into image chunks (H2D / conv1_1 and last op / D2H overlap); the result
     must be bit-identical to the single-shot device-pointer path, for pinned and pageable caller memory."""
