@@ -337,3 +337,30 @@ def test_host_pipeline_matches_device_path(synth_sd, n, pinned):
         assert np.array_equal(r["ab"], ref_ab) and np.array_equal(r["rgb"], ref_rgb)
     assert ctx.last_launch_count() > 27                 # conv1_1 and the last op ran once per chunk
     ctx.close()
+
+
+def test_headless_cli_writes_the_gui_result_folder(synth_sd, tmp_path):
+    """ideepcolor_b200.py (row f4): hint list in, the reference GUI's save_result artefacts out."""
+    import json
+    import cv2
+    import ideepcolor_b200
+    g = util.golden("lhn_256.npz")
+    img = tmp_path / "in.png"
+    cv2.imwrite(str(img), np.ascontiguousarray(g["img_rgb"][:, :, ::-1]))
+    wts = tmp_path / "w.pth"
+    torch.save(synth_sd, str(wts))
+    hints = tmp_path / "hints.json"
+    hints.write_text(json.dumps([{"loc": [135, 160], "size": 3, "ab": [23, -69]}, {"loc": [100, 160], "rgb": [255, 255, 255]}]))
+    out = tmp_path / "res"
+    rc = ideepcolor_b200.main(["--image_file", str(img), "--color_model", str(wts), "--hints", str(hints),
+                               "--out", str(out), "--suggest", "5"])
+    assert rc == 0
+    for f in ("im_l.npy", "im_ab.npy", "im_mask.npy", "input_mask.png", "ours.png", "ours_fullres.png",
+              "input_fullres.png", "input.png", "input_ab.png", "suggestions.json"):
+        assert (out / f).exists(), f
+    ab = np.load(str(out / "im_ab.npy"))
+    assert ab.shape == (2, 256, 256) and np.allclose(ab[:, 135, 160], [23, -69]) and np.abs(ab[:, 100, 160]).max() < 0.5
+    ours = cv2.imread(str(out / "ours.png"))
+    assert ours.shape == (256, 256, 3)
+    sug = json.load(open(str(out / "suggestions.json")))
+    assert len(sug) == 2 and np.array(sug[0]["ab"]).shape == (5, 2) and abs(sum(sug[0]["conf"]) - 1) < 1e-3
