@@ -71,3 +71,14 @@ def test_reccs_are_sorted_by_mass():
     centers, conf = cd.get_ab_reccs(5, 5, K=3, N=5000, return_conf=True, method='sampled')
     assert np.allclose(centers[0], cd.pts_in_hull[10]) and np.allclose(centers[2], cd.pts_in_hull[500])
     assert conf[0] > conf[1] > conf[2] and abs(conf.sum() - 1) < 1e-9
+
+
+def test_headless_cli_hint_parsing():
+    import ideepcolor_b200 as cli
+    a = cli.parse_args(["--color_model", "w.pth", "--suggest", "9", "--pytorch_maskcent"])
+    assert a.load_size == 256 and a.suggest == 9 and a.pytorch_maskcent and a.gpu == 0
+    assert cli.hint_ab({"ab": [23, -69]}) == [23.0, -69.0]
+    white = cli.hint_ab({"rgb": [255, 255, 255]})
+    assert abs(white[0]) < 0.01 and abs(white[1]) < 0.01
+    red = cli.hint_ab({"rgb": [255, 0, 0]})
+    assert abs(red[0] - 80.09) < 0.05 and abs(red[1] - 67.20) < 0.05      # sRGB red in CIELAB (D65)
