@@ -156,8 +156,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "256x256 synthetic L + sparse hints, CPU oracle port of SIGGRAPHGenerator.forward, "
-                                   "%d single-image calls per step (reference has no batch API)" % per_step},
+            "config": {"workload": "BASELINE config 3: 64 x 256x256 synthetic L + 0-10 sparse 7x7 ab hints per GPU, "
+                                   "regression head (ab map)",
+                       "sample": "bounded: %d single-image calls of the CPU oracle port of SIGGRAPHGenerator.forward per step, "
+                                 "images drawn from that workload (the reference has no batch API, model.py:139-141)" % per_step},
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": thr, "kind": "port",
                              "sample": "%d images (batch-1 loop), torch CPU fp32, best-of pool sizes -> %d threads of %d host cores"
                                        % (n, thr, os.cpu_count() or 0)},
