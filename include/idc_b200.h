@@ -105,8 +105,10 @@ int idc_forward(idc_ctx* ctx, int n, int h, int w, const float* L_mc, const floa
                 const float* mask, float maskcent, const float* glob, float* out_ab,
                 float* out_dist, uint8_t* out_rgb, void* stream);
 
-/* Same with HOST pointers (pinned staging inside; synchronous).  This is the call the
- * reference-facing wrapper and bench.py's e2e leg use. */
+/* Same with HOST pointers (pinned staging inside unless the caller's buffers are already pinned;
+ * synchronous).  This is the call the reference-facing wrapper and bench.py's e2e leg use.  Batches <= 4
+ * replay a CUDA graph; batches >= 8 overlap the copies with the first / last layer in image chunks
+ * (results are bit-identical to idc_forward). */
 int idc_forward_host(idc_ctx* ctx, int n, int h, int w, const float* L_mc, const float* ab,
                      const float* mask, float maskcent, const float* glob, float* out_ab,
                      float* out_dist, uint8_t* out_rgb);
