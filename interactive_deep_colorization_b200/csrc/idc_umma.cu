@@ -68,6 +68,7 @@ struct UmmaParams {
   float out_mult;
   int* err;
   long long* dbgbuf;   // experiments only: per-CTA cycle counters [grid][8]
+  int halo_groups;     // HALO kernels: 64-channel input groups (K = 9 taps x halo_groups k-blocks); kblk = {-, B k-column, dy+1, dx+1}
   int img0;            // first image of this launch (n_img = img0 + images of the launch): idc_forward_host
                        // runs the last op in image chunks so that the D2H of a chunk overlaps the next one
 };
@@ -235,10 +236,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // K-major, 128-byte-swizzled operand tile: rows of 64 FP16 (128 B), 8-row swizzle atoms 1024 B
 // apart (SBO); LBO unused for a single K atom.  Bit layout = cute::UMMA::SmemDescriptor.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t sbo = 1024u) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);  // start address
-  d |= (uint64_t)(1024u >> 4) << 32;            // stride byte offset
+  d |= (uint64_t)(sbo >> 4) << 32;              // stride byte offset (pitch of the 8-row groups)
   d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
   d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
   return d;
@@ -274,16 +275,26 @@ __device__ __forceinline__ void split_h(float v, __half& hi, __half& lo) {
   lo = __float2half_rn(v - __half2float(hi));
 }
 
-template <int BN, int MT, int CG, bool SPLIT>
+// HALO (stride-1 3x3 layers): instead of one TMA box per filter tap, ONE halo tile of 18 rows x 10 pixels per
+// 64-channel input group serves all 9 taps of a 16-row x 8-pixel M-tile -- the MMA's A descriptor starts at the
+// pixel-shifted window (start = slot + ((dy+1)*10 + dx+1)*128 B, SBO = 10*128 B; the 128-byte swizzle is a function
+// of the absolute smem address: tools/experiments/halo_desc_probe.cu).  The stage ring then holds weight tiles only.
+constexpr int kHaloW = 10, kHaloH = 18;
+constexpr int kHaloPlane = (kHaloW * kHaloH * 128 + 1023) / 1024 * 1024;   // 23040 -> 23552
+template <int BN, int MT, int CG, bool SPLIT, bool HALO = false>
 struct SmemPlan {
   static constexpr int kABytes = MT * kBM * kBK * 2;            // MT M-tiles of 128 pixels x 64 ch FP16 (16 KB each)
+  static constexpr int kAStage = HALO ? 0 : kABytes;           // A bytes inside a ring stage (one plane)
   static constexpr int kBBytes = (BN / CG) * kBK * 2;          // CG == 2: each CTA of the pair holds half of the weight tile
-  static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kBBytes);
+  static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kAStage + kBBytes);
+  static constexpr int kHaloSlot = (SPLIT ? 2 : 1) * kHaloPlane;
+  static constexpr int kHaloBytes = HALO ? 2 * kHaloSlot : 0;   // two halo slots (double buffered)
+  static_assert(!HALO || MT == 1, "halo tiles are single 16x8-pixel M-tiles");
   static constexpr int kTail = 3 * BN * 4 + 272 * 4 + 256 + 128 * 2 * 4;  // epi vecs, head, barriers, head reduce
   static constexpr int kOutStage = 16384;                         // epilogue staging: one private 2 KB transpose tile per accumulate warp
-  static constexpr int kBudget = 232448 - 1024 - kTail - kOutStage;  // 227 KB opt-in limit minus alignment slack
+  static constexpr int kBudget = 232448 - 1024 - kTail - kOutStage - kHaloBytes;  // 227 KB opt-in limit minus alignment slack
   static constexpr int kStages = kBudget / kStageBytes >= 4 ? 4 : kBudget / kStageBytes;
-  static constexpr int kTotal = kStages * kStageBytes + kOutStage + kTail + 1024;   // + alignment slack
+  static constexpr int kTotal = kStages * kStageBytes + kHaloBytes + kOutStage + kTail + 1024;   // + alignment slack
   static constexpr int kBufCols = MT * BN;                       // TMEM columns of one chunk buffer
   static constexpr int kNBuf = (512 / kBufCols) >= 4 ? 4 : (512 / kBufCols);
   static constexpr int kTmemCols = (kNBuf * kBufCols <= 128) ? 128 : (kNBuf * kBufCols <= 256 ? 256 : 512);
@@ -295,16 +306,17 @@ struct SmemPlan {
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <int BN, int MT, int CG, bool SPLIT>
+template <int BN, int MT, int CG, bool SPLIT, bool HALO = false>
 __global__ void __launch_bounds__(kThreads, 1)
 umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_constant__ CUtensorMap bmap_lo,
                  const UmmaParams p) {
-  using SP = SmemPlan<BN, MT, CG, SPLIT>;
+  using SP = SmemPlan<BN, MT, CG, SPLIT, HALO>;
   constexpr int STAGES = SP::kStages;
   constexpr bool PAIR = CG == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_out = smem + STAGES * SP::kStageBytes;              // 1024-aligned (stage sizes are multiples of 1 KB)
+  uint8_t* s_halo = smem + STAGES * SP::kStageBytes;             // HALO: 2 slots x {hi, lo} planes, 1024-aligned
+  uint8_t* s_out = s_halo + SP::kHaloBytes;                      // 1024-aligned (stage / plane sizes are multiples of 1 KB)
   uint8_t* tail = s_out + SP::kOutStage;
   float* s_bias = reinterpret_cast<float*>(tail);
   float* s_scale = s_bias + BN;
@@ -317,6 +329,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
   uint64_t* tfull_bar = s_bar + 2 * STAGES;        // [NBUF]   MMA -> accumulate warps (chunk ready)
   uint64_t* tempty_bar = s_bar + 2 * STAGES + NBUF;  // [NBUF] accumulate warps -> MMA (chunk drained)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * STAGES + 2 * NBUF);
+  uint64_t* afull_bar = s_bar + 20;                // [2] HALO: halo TMA -> MMA
+  uint64_t* aempty_bar = s_bar + 22;               // [2] HALO: MMA -> halo TMA
   float* s_red = reinterpret_cast<float*>(s_bar + 32);   // [128][2] fused-head partial sums, after the 256-byte barrier block
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -337,6 +351,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       mbar_init(smem_u32(&tfull_bar[a]), 1);
       mbar_init(smem_u32(&tempty_bar[a]), 8 * CG);  // one arrive per accumulate warp (of both CTAs on the leader)
     }
+    if (HALO)
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(smem_u32(&afull_bar[a]), CG);
+        mbar_init(smem_u32(&aempty_bar[a]), 1);
+      }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (PAIR) cluster_sync_all();                      // peer barriers exist before anything can arrive on them
@@ -369,6 +388,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
     {
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t hcount = 0;                               // HALO: halo loads issued (slot = hcount & 1)
       for (int w = blockIdx.x / CG; w < p.total_tiles * S; w += gridDim.x / CG) {
         const int tile = w / S, ks = w - tile * S;
         const int kbeg = (ks * p.nkb) / S, kend = ((ks + 1) * p.nkb) / S;
@@ -387,6 +407,50 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         const int y0 = (r / p.tiles_x) * (p.hbox * MT), x0 = (r % p.tiles_x) * p.wbox;
         const int brow = cls * p.cout_pad + nt * BN + (int)cta_rank * (BN / CG);
         const int4* kb = p.kblk + cls * p.nkb;                  // read-only table in global memory (L1-resident)
+        if (HALO) {
+          // k-block i = (input group i / 9, tap i % 9): one halo load per group, one weight tile per k-block
+          for (int k = kbeg; k < kend; ++k) {
+            if (k % 9 == 0) {
+              const uint32_t slot = hcount & 1, hphase = (hcount >> 1) & 1;
+              ++hcount;
+              mbar_wait(smem_u32(&aempty_bar[slot]), hphase ^ 1, p.err, 6);
+              if (elect_one()) {
+                const uint32_t fa = smem_u32(&afull_bar[slot]);
+                const uint32_t sh = smem_u32(s_halo + slot * SP::kHaloSlot);
+                const int c0 = (k / 9) * kBK;
+                constexpr uint32_t kHaloTx = (SPLIT ? 2 : 1) * kHaloW * kHaloH * 128;
+                if (PAIR) {
+                  if (leader) mbar_expect_tx(fa, 2 * kHaloTx); else mbar_arrive_rank0(fa);
+                  tma_load_4d_pair(sh, p.amaps, fa, c0, x0 - 1, y0 - 1, img);
+                  if (SPLIT) tma_load_4d_pair(sh + kHaloPlane, p.amaps + 1, fa, c0, x0 - 1, y0 - 1, img);
+                } else {
+                  mbar_expect_tx(fa, kHaloTx);
+                  tma_load_4d(sh, p.amaps, fa, c0, x0 - 1, y0 - 1, img);
+                  if (SPLIT) tma_load_4d(sh + kHaloPlane, p.amaps + 1, fa, c0, x0 - 1, y0 - 1, img);
+                }
+              }
+              __syncwarp();
+            }
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 1);
+            if (elect_one()) {
+              const uint32_t fb = smem_u32(&full_bar[stage]);
+              const int4 e = __ldg(kb + k);
+              const uint32_t sb = smem_u32(smem + stage * SP::kStageBytes);
+              if (PAIR) {
+                if (leader) mbar_expect_tx(fb, 2 * SP::kStageBytes); else mbar_arrive_rank0(fb);
+                tma_load_2d_pair(sb, &bmap_hi, fb, e.y, brow);
+                if (SPLIT) tma_load_2d_pair(sb + SP::kBBytes, &bmap_lo, fb, e.y, brow);
+              } else {
+                mbar_expect_tx(fb, SP::kStageBytes);
+                tma_load_2d(sb, &bmap_hi, fb, e.y, brow);
+                if (SPLIT) tma_load_2d(sb + SP::kBBytes, &bmap_lo, fb, e.y, brow);
+              }
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (!HALO)
         for (int k = kbeg; k < kend; ++k) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 1);
           if (elect_one()) {
@@ -422,6 +486,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       uint32_t cc = 0;                                   // chunk counter (persists across tiles)
+      uint32_t hcount = 0;                               // HALO: halo tiles consumed
       long long t_wait_tempty = 0, t_wait_full = 0;
       const long long t_start = clock64();
       for (int w = blockIdx.x / CG; w < p.total_tiles * S; w += gridDim.x / CG) {
@@ -438,19 +503,33 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           const int k1 = (k0 + G < kend) ? k0 + G : kend;
           for (int k = k0; k < k1; ++k) {
             const long long tB = (IDC_CTA_COUNTERS && p.dbgbuf) ? clock64() : 0;
+            uint32_t hslot = 0;
+            if (HALO) {
+              if (k % 9 == 0) {
+                mbar_wait(smem_u32(&afull_bar[hcount & 1]), (hcount >> 1) & 1, p.err, 7);
+                ++hcount;
+              }
+              hslot = (hcount - 1) & 1;
+            }
             mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 3);
             if (IDC_CTA_COUNTERS && p.dbgbuf) t_wait_full += clock64() - tB;
             tc_fence_after();
             if (elect_one()) {
             const uint32_t sa = smem_u32(smem + stage * SP::kStageBytes);
-            const uint32_t sb = sa + (SPLIT ? 2 : 1) * SP::kABytes;
+            const uint32_t sb = sa + (SPLIT ? 2 : 1) * SP::kAStage;
             const uint64_t b_hi = make_sw128_desc(sb);
             const uint64_t b_lo = make_sw128_desc(sb + SP::kBBytes);
             const uint32_t fresh = (k == k0) ? 0u : 1u;    // first MMA into a chunk buffer overwrites it
+            uint32_t ha = 0;                               // HALO: this tap's window inside the halo slot
+            if (HALO) {
+              const int4 e = __ldg(p.kblk + k);
+              ha = smem_u32(s_halo + hslot * SP::kHaloSlot) + (uint32_t)(e.z * kHaloW + e.w) * 128u;
+            }
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-              const uint64_t a_hi = make_sw128_desc(sa + mt * (kBM * kBK * 2));
-              const uint64_t a_lo = make_sw128_desc(sa + SP::kABytes + mt * (kBM * kBK * 2));
+              const uint64_t a_hi = HALO ? make_sw128_desc(ha, kHaloW * 128) : make_sw128_desc(sa + mt * (kBM * kBK * 2));
+              const uint64_t a_lo = HALO ? make_sw128_desc(ha + kHaloPlane, kHaloW * 128)
+                                         : make_sw128_desc(sa + SP::kABytes + mt * (kBM * kBK * 2));
               const uint32_t d = d_tmem + mt * BN;
               uint32_t first = fresh;
               if (SPLIT) {
@@ -479,9 +558,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
             }
             if (PAIR) {
               umma_commit_pair(smem_u32(&empty_bar[stage]));                       // both CTAs' stages
+              if (HALO && k % 9 == 8) umma_commit_pair(smem_u32(&aempty_bar[hslot]));   // both CTAs' halo slots
               if (k == k1 - 1) umma_commit_pair(smem_u32(&tfull_bar[buf]));        // both CTAs' accumulate warps
             } else {
               umma_commit(smem_u32(&empty_bar[stage]));   // frees the smem stage when these MMAs retire
+              if (HALO && k % 9 == 8) umma_commit(smem_u32(&aempty_bar[hslot]));
               if (k == k1 - 1) umma_commit(smem_u32(&tfull_bar[buf]));   // chunk complete -> accumulate warps
             }
             }
@@ -828,6 +909,7 @@ struct UmmaPlan {
   int mt = 1;               // M-tiles (128 pixels each) per CTA tile
   int cg = 1;               // 2: CTA pairs (cta_group::2), one 256x256 output tile per pair
   int split_k = 1;
+  bool halo = false;        // one halo tile per input-channel group instead of one TMA box per tap (stride-1 3x3 layers)
   size_t ws_floats = 0;
   int ws_tiles = 0;
 };
@@ -839,12 +921,12 @@ struct ViewKey {
 
 static int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
-template <int BN, int MT, int CG, bool SPLIT>
+template <int BN, int MT, int CG, bool SPLIT, bool HALO = false>
 static cudaError_t launch_inst(const UmmaPlan& pl, const UmmaParams& prm, cudaStream_t st) {
-  using SP = SmemPlan<BN, MT, CG, SPLIT>;
+  using SP = SmemPlan<BN, MT, CG, SPLIT, HALO>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<BN, MT, CG, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<BN, MT, CG, SPLIT, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SP::kTotal);
     if (e != cudaSuccess) return e;
     attr = true;
@@ -861,7 +943,7 @@ static cudaError_t launch_inst(const UmmaPlan& pl, const UmmaParams& prm, cudaSt
   at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = CG > 1 ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, umma_conv_kernel<BN, MT, CG, SPLIT>, pl.bmap_hi, pl.bmap_lo, prm);
+  return cudaLaunchKernelEx(&cfg, umma_conv_kernel<BN, MT, CG, SPLIT, HALO>, pl.bmap_hi, pl.bmap_lo, prm);
 }
 
 int umma_plan_op(Ctx* c, ConvOp& op) {
@@ -882,21 +964,42 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
     const int t = ceil_div(op.Wl, wb) * ceil_div(op.Hl, hb);
     if (t < best) { best = t; op.wbox = wb; op.hbox = hb; }
   }
+  // HALO (experimental, IDC_HALO=1; =3 also on launches that do not fill the machine, for the unit tests): stride-1
+  // 3x3 convs of one source with <= 128 output columns per tile load one 18x10-pixel halo tile per 64 input
+  // channels instead of one box per tap.
+  {
+    int mode = 0;
+    if (const char* e = getenv("IDC_HALO")) mode = atoi(e);
+    bool ok = mode >= 1 && !c->fast && op.ncls == 1 && op.ntaps == 9 && op.bn_tile <= 128;
+    unsigned seen = 0;
+    for (int t = 0; ok && t < op.ntaps; ++t) {
+      const Tap& tp = op.taps[0][t];
+      if (tp.src != op.taps[0][0].src || op.src[tp.src].s != 1 || tp.ty < -1 || tp.ty > 1 || tp.tx < -1 || tp.tx > 1) ok = false;
+      else seen |= 1u << ((tp.ty + 1) * 3 + tp.tx + 1);
+    }
+    if (ok && (seen != 0x1FFu || op.src[op.taps[0][0].src].cin % kBK)) ok = false;
+    if (ok) {   // only launches that fill the machine (no split-K on this path)
+      const long T = (long)c->max_n * ceil_div(op.Hl, 16) * ceil_div(op.Wl, 8) * (op.cout_pad / op.bn_tile);
+      if (T < 2L * pl->num_sms && mode < 3) ok = false;
+    }
+    pl->halo = ok;
+    if (ok) { op.wbox = 8; op.hbox = 16; }
+  }
   // Two M-tiles per CTA tile (one 256-pixel TMA box, two MMAs sharing each B tile) for the narrow-N layers:
   // halves the weight re-streaming and the per-k-block hand-off overhead.  Only when the launch still
   // fills the machine at the ctx's max batch (the batch-1 latency ctx keeps 128-pixel tiles).
   pl->mt = 1;
-  if (op.bn_tile <= 128) {
+  if (op.bn_tile <= 128 && !pl->halo) {
     const long tiles2 = (long)op.ncls * c->max_n * ceil_div(op.Hl, 2 * op.hbox) * ceil_div(op.Wl, op.wbox) *
                         (op.cout_pad / op.bn_tile);
     if (tiles2 >= 2L * pl->num_sms && op.hbox * 2 <= 256) pl->mt = 2;
   }
-  if (const char* e = getenv("IDC_MT")) { int v = atoi(e); if (v == 1 || (v == 2 && op.bn_tile <= 128)) pl->mt = v; }
+  if (const char* e = getenv("IDC_MT")) { int v = atoi(e); if (!pl->halo && (v == 1 || (v == 2 && op.bn_tile <= 128))) pl->mt = v; }
   // CTA pairs for the 256-wide tiles when the launch is large (never on the split-K / batch-1 path)
   pl->cg = 1;
   {
     const long tiles1 = (long)op.ncls * c->max_n * ceil_div(op.Hl, op.hbox) * ceil_div(op.Wl, op.wbox) * (op.cout_pad / op.bn_tile);
-    const bool can = !c->fast && (op.bn_tile == 256 || op.bn_tile == 128 || (op.bn_tile == 64 && pl->mt == 2));
+    const bool can = !c->fast && (op.bn_tile == 256 || op.bn_tile == 128 || (op.bn_tile == 64 && (pl->mt == 2 || pl->halo)));
     const long tiles_mt = tiles1 / pl->mt;
     int mode = 1;          // IDC_PAIRS: 0 = off, 1 (default) = launches that give every SM pair >= 2 tiles, 2 = always
     if (const char* e = getenv("IDC_PAIRS")) mode = atoi(e);
@@ -906,7 +1009,16 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   std::vector<ViewKey> views;
   const int nkb = op.K / kBK;
   std::vector<int4> kblk((size_t)op.ncls * nkb);
-  for (int cls = 0; cls < op.ncls; ++cls) {
+  if (pl->halo) {
+    // k-block i = (input group i / 9, tap i % 9); entry = {-, K column of the weight tile, dy + 1, dx + 1}
+    const int src = op.taps[0][0].src, groups = op.src[src].cin / kBK;
+    views.push_back(ViewKey{src, 1, 0, 0});
+    for (int i = 0; i < nkb; ++i) {
+      const int g = i / 9, t = i % 9;
+      kblk[i] = make_int4(0, (t * groups + g) * kBK, op.taps[0][t].ty + 1, op.taps[0][t].tx + 1);
+    }
+  }
+  for (int cls = 0; cls < op.ncls && !pl->halo; ++cls) {
     int kb = 0;
     for (int t = 0; t < op.ntaps; ++t) {
       const Tap& tp = op.taps[cls][t];
@@ -940,7 +1052,8 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
       cuuint64_t dims[4] = {(cuuint64_t)b.C, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)c->max_n};
       cuuint64_t strides[3] = {(cuuint64_t)vk.s * b.C * 2, (cuuint64_t)vk.s * b.W * b.C * 2,
                                (cuuint64_t)b.H * b.W * b.C * 2};
-      cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)op.wbox, (cuuint32_t)(op.hbox * pl->mt), 1};
+      cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(pl->halo ? kHaloW : op.wbox),
+                           (cuuint32_t)(pl->halo ? kHaloH : op.hbox * pl->mt), 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = enc(&amaps[i * 2 + part], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -980,6 +1093,7 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
 
   UmmaParams& q = pl->prm;
   q.amaps = pl->d_amaps; q.kblk = pl->d_kblk; q.nkb = nkb; q.ncls = op.ncls;
+  q.halo_groups = pl->halo ? nkb / 9 : 0;
   {
     // chunk_kb: k-blocks summed inside the tensor core before the FP32 round-to-nearest add.
     // 1 is the most accurate (1.5e-4 ab error end to end, 3.4e-4 with 2 everywhere -- profiles/).
@@ -1016,7 +1130,7 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   {
     const long T = (long)op.ncls * c->max_n * q.tiles_y * q.tiles_x * q.n_tiles_n;
     int S = 1;
-    if (T * 2 <= pl->num_sms && nkb >= 8 && !op.fuse_out_head && pl->mt == 1 && pl->cg == 1) {
+    if (T * 2 <= pl->num_sms && nkb >= 8 && !op.fuse_out_head && pl->mt == 1 && pl->cg == 1 && !pl->halo) {
       S = (int)(pl->num_sms / T);
       if (S > nkb / 4) S = nkb / 4;
       if (S > op.bn_tile / 32) S = op.bn_tile / 32;      // one 32-column piece per CTA at least
@@ -1024,7 +1138,7 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
     }
     if (const char* e = getenv("IDC_SPLIT_K")) {           // experiments; must keep all work items co-resident
       int v = atoi(e);
-      if (v >= 1 && v <= nkb && v <= op.bn_tile / 32 && pl->mt == 1 && T * v <= pl->num_sms) S = v;
+      if (v >= 1 && v <= nkb && v <= op.bn_tile / 32 && pl->mt == 1 && !pl->halo && T * v <= pl->num_sms) S = v;
     }
     pl->split_k = S;
     pl->ws_tiles = (int)T;
@@ -1071,6 +1185,16 @@ cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float ou
   const bool split = !c->fast;
 #define IDC_LAUNCH(BN_, MT_, CG_)                                              \
   return split ? launch_inst<BN_, MT_, CG_, true>(*pl, prm, st) : launch_inst<BN_, MT_, CG_, false>(*pl, prm, st)
+  if (pl->halo) {
+    if (!split) return cudaErrorInvalidValue;
+    switch (op.bn_tile * 10 + pl->cg) {
+      case 641: return launch_inst<64, 1, 1, true, true>(*pl, prm, st);
+      case 642: return launch_inst<64, 1, 2, true, true>(*pl, prm, st);
+      case 1281: return launch_inst<128, 1, 1, true, true>(*pl, prm, st);
+      case 1282: return launch_inst<128, 1, 2, true, true>(*pl, prm, st);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (op.bn_tile * 100 + pl->mt * 10 + pl->cg) {
     case 6411: IDC_LAUNCH(64, 1, 1);
     case 6421: IDC_LAUNCH(64, 2, 1);
