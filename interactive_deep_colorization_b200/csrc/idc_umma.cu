@@ -964,13 +964,16 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
     const int t = ceil_div(op.Wl, wb) * ceil_div(op.Hl, hb);
     if (t < best) { best = t; op.wbox = wb; op.hbox = hb; }
   }
-  // HALO (experimental, IDC_HALO=1; =3 also on launches that do not fill the machine, for the unit tests): stride-1
-  // 3x3 convs of one source with <= 128 output columns per tile load one 18x10-pixel halo tile per 64 input
-  // channels instead of one box per tap.
+  // HALO: stride-1 3x3 convs of one source with 128 output columns per tile (c2_2, c9_2, c10_2: the layers that are
+  // shared-memory-bandwidth bound with per-tap boxes) load one 18x10-pixel halo tile per 64 input channels instead of
+  // one box per tap, when the launch fills the machine.  Measured at 64 x 256^2: c2_2 0.76 -> 0.63 ms, c9_2 0.76 ->
+  // 0.63, c10_2 2.44 -> 2.28; the 64-column c1_2 gets slower (1.11 -> 1.17: its weight tile is re-streamed per 128
+  // instead of 256 pixels) and keeps the per-tap path.  IDC_HALO=0 turns it off, =3 forces it on every eligible op
+  // (also 64 columns, also tiny launches) for the unit tests.
   {
-    int mode = 0;
+    int mode = 1;
     if (const char* e = getenv("IDC_HALO")) mode = atoi(e);
-    bool ok = mode >= 1 && !c->fast && op.ncls == 1 && op.ntaps == 9 && op.bn_tile <= 128;
+    bool ok = mode >= 1 && !c->fast && op.ncls == 1 && op.ntaps == 9 && (op.bn_tile == 128 || (mode >= 3 && op.bn_tile == 64));
     unsigned seen = 0;
     for (int t = 0; ok && t < op.ntaps; ++t) {
       const Tap& tp = op.taps[0][t];

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
                 ids=["mt1", "mt2", "pairs", "pairs_mt2", "halo", "halo_pairs"])
 def setup(request, synth_sd):
     """(IDC_MT, IDC_PAIRS, IDC_HALO) are read when the launch plan is built: the 128-pixel tiles, the 256-pixel
-    tiles, the cta_group::2 pair path (forced, incl. the odd-tile-count dummy tile) and the experimental halo-tile
+    tiles, the cta_group::2 pair path (forced, incl. the odd-tile-count dummy tile) and the halo-tile
     A operand (one TMA tile per 64 input channels + pixel-shifted UMMA descriptors, stride-1 3x3 layers with
     <= 128 output columns) are exercised on every op that supports them."""
     import os
