@@ -70,6 +70,21 @@ const char* idc_version(void);
  * (data/colorize_image.py:221,230-232).  max_n = largest batch a forward may carry. */
 int idc_create(int device, int max_n, int h, int w, unsigned flags, idc_ctx** out);
 
+/* Plan-time options (replace the IDC_* environment switches of round 1; a library embedded in another process
+ * must not read process-global state).  Call between idc_create and idc_finalize_weights / idc_adopt_weights;
+ * a later call re-plans the launches.  -1 = automatic where it applies.
+ *   "halo"          0 / 1 / 3   halo-tile A operand (one TMA tile per 64 input channels serves all 9 taps)
+ *   "pairs"         0 / 1 / 2   cta_group::2 CTA pairs: never / large launches / always
+ *   "mt"            1 / 2       128-pixel M-tiles per CTA tile on the <= 128-column layers
+ *   "chunk_kb"      >= 1        k-blocks summed in TMEM before the FP32 round-to-nearest add (accuracy vs speed)
+ *   "split_k"       >= 1        K slices per tile on launches that cannot fill the machine
+ *   "split_pairs"   0 / 1       run the split-K (small batch) launches as CTA pairs
+ *   "direct_stores" 0 / 1       per-lane 16-byte stores instead of the warp-transposed ones
+ *   "host_pipe"     0 / 1       idc_forward_host: chunked copy/compute overlap for batches >= 8
+ *   "pdl"           0 / 1       programmatic dependent launch between the kernels of one forward
+ * Unknown names return IDC_ERR_KEY. */
+int idc_set_option(idc_ctx* ctx, const char* name, int value);
+
 /* Replaces one entry of `self.net.load_state_dict(state_dict)` (data/colorize_image.py:229).
  * key = reference state_dict key ("model1.0.weight", "model1.4.running_var", ...; conv OIHW,
  * deconv IOHW, model.py:13-108).  Extra keys accepted with IDC_FLAG_GLOBAL_HINTS:
@@ -105,13 +120,21 @@ int idc_forward(idc_ctx* ctx, int n, int h, int w, const float* L_mc, const floa
                 const float* mask, float maskcent, const float* glob, float* out_ab,
                 float* out_dist, uint8_t* out_rgb, void* stream);
 
-/* Same with HOST pointers (pinned staging inside unless the caller's buffers are already pinned;
- * synchronous).  This is the call the reference-facing wrapper and bench.py's e2e leg use.  Batches <= 4
- * replay a CUDA graph; batches >= 8 overlap the copies with the first / last layer in image chunks
- * (results are bit-identical to idc_forward). */
+/* Same with HOST pointers (synchronous).  This is the call the reference-facing wrapper and bench.py's e2e leg use.
+ * Batches <= 4 (the interactive click) replay ONE CUDA graph: a single H2D of the staged inputs, the kernels chained by
+ * programmatic dependent launch, a single D2H of the results; batches >= 8 copy straight from / to pinned caller
+ * buffers (pageable ones are staged) and overlap the copies with the first / last layer in image chunks.
+ * Results are bit-identical to idc_forward. */
 int idc_forward_host(idc_ctx* ctx, int n, int h, int w, const float* L_mc, const float* ab,
                      const float* mask, float maskcent, const float* glob, float* out_ab,
                      float* out_dist, uint8_t* out_rgb);
+/* Same + the reference's QUANTISED `self.output_ab` (row a11): out_abq [n,2,h,w] float64 =
+ * rgb2lab(out_rgb)[1:] (`_set_out_ab_`, data/colorize_image.py:196-198,267; what the GUI and get_img_fullres read,
+ * ui/gui_draw.py:280, :123-131), computed on the device from the just-quantised uint8 pixel, so the wrapper's
+ * net_forward is ONE call and one round trip.  out_abq needs out_rgb; NULL = idc_forward_host. */
+int idc_forward_host_q(idc_ctx* ctx, int n, int h, int w, const float* L_mc, const float* ab,
+                       const float* mask, float maskcent, const float* glob, float* out_ab,
+                       float* out_dist, uint8_t* out_rgb, double* out_abq);
 
 /* Interactive path: keep the 529-bin distribution of the last idc_forward_host on the device instead
  * of copying all of it back (8.7 MB at 256^2) -- the reference only ever reads one pixel of it per click

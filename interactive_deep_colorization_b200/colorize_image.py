@@ -199,12 +199,29 @@ class ColorizeImageB200(ColorizeImageBase):
         B = np.ascontiguousarray(self.input_ab_mc, dtype=np.float32)[None]
         M = np.ascontiguousarray(self.input_mask_mult, dtype=np.float32)[None]
         ctx = self.net._context(A.shape[-2], A.shape[-1], 1)
-        # one C-ABI call: H2D, forward, fused Lab->RGB post-process (reference :263-264), D2H
-        r = ctx.forward_host(A, B, M, float(self.mask_cent), want_dist=False, want_rgb=True)
+        # ONE C-ABI call and one round trip: H2D, forward, fused Lab->RGB post-process (reference :263-264) and the
+        # quantised output_ab = rgb2lab(output_rgb)[1:] (reference :267 -> :196-198) in the same kernel, D2H
+        r = ctx.forward_host(A, B, M, float(self.mask_cent), want_dist=False, want_rgb=True, want_abq=self.gpu_prepost)
         self.output_ab_raw = r["ab"][0]          # raw net output (the parity quantity)
         self.output_rgb = r["rgb"][0]
-        self._set_out_ab_()
+        if self.gpu_prepost:
+            self.output_ab = r["abq"][0]
+            self._output_lab = None              # output_lab (L plane included) is derived on demand
+        else:
+            self._set_out_ab_()
         return self.output_rgb
+
+    @property
+    def output_lab(self):
+        """reference :197 (`self.output_lab = rgb2lab_transpose(self.output_rgb)`); nothing in the reference reads it
+        besides `_set_out_ab_` itself, so the fused path computes it lazily."""
+        if getattr(self, "_output_lab", None) is None:
+            self._output_lab = rgb2lab_transpose(self.output_rgb)
+        return self._output_lab
+
+    @output_lab.setter
+    def output_lab(self, v):
+        self._output_lab = v
 
     def get_img_forward(self):
         return self.output_rgb
@@ -213,18 +230,24 @@ class ColorizeImageB200(ColorizeImageBase):
         return lab2rgb_transpose(self.img_l, np.zeros((2, self.Xd, self.Xd)))
 
     # ----- row f1: the numpy/scipy steps either side of the network, on the GPU when a net is set -----
+    def _device(self):
+        """CUDA device ordinal of the engine behind this wrapper (the Torch-named classes hold a module in
+        `self.net`, the GlobDist / Caffe-named ones an LhnContext in `self._ctx`)."""
+        ctx = getattr(self, "_ctx", None)
+        return ctx.device if ctx is not None else self.net.b200_device
+
     def _set_out_ab_(self):
         if not (self.gpu_prepost and self.net_set):
             return ColorizeImageBase._set_out_ab_(self)
         from . import prepost
-        self.output_lab = prepost.rgb2lab_gpu(self.output_rgb, self.net.b200_device)
+        self.output_lab = prepost.rgb2lab_gpu(self.output_rgb, self._device())
         self.output_ab = self.output_lab[1:]
 
     def get_img_fullres(self):
         if not (self.gpu_prepost and self.net_set):
             return ColorizeImageBase.get_img_fullres(self)
         from . import prepost
-        return prepost.fullres_rgb_gpu(self.output_ab, self.img_l_fullres, self.net.b200_device)
+        return prepost.fullres_rgb_gpu(self.output_ab, self.img_l_fullres, self._device())
 
 
 class _LazyUpsampledDist(object):
@@ -378,8 +401,12 @@ class ColorizeImageB200GlobDist(ColorizeImageB200):
         A = np.ascontiguousarray(self.img_l_mc, dtype=np.float32)[None]
         B = np.ascontiguousarray(self.input_ab_mc, dtype=np.float32)[None]
         M = np.ascontiguousarray(self.input_mask_mult, dtype=np.float32)[None]
-        r = self._ctx.forward_host(A, B, M, float(self.mask_cent), glob=glob, want_rgb=True)
+        r = self._ctx.forward_host(A, B, M, float(self.mask_cent), glob=glob, want_rgb=True, want_abq=self.gpu_prepost)
         self.output_ab_raw = r["ab"][0]
         self.output_rgb = r["rgb"][0]
-        ColorizeImageBase._set_out_ab_(self)
+        if self.gpu_prepost:
+            self.output_ab = r["abq"][0]
+            self._output_lab = None
+        else:
+            ColorizeImageBase._set_out_ab_(self)
         return self.output_rgb

@@ -488,9 +488,11 @@ struct HostPipe {
 };
 
 int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mask, float maskcent, const float* glob,
-                float* out_ab, float* out_dist, uint8_t* out_rgb, cudaStream_t st, const HostPipe* hp = nullptr) {
+                float* out_ab, float* out_dist, uint8_t* out_rgb, cudaStream_t st, const HostPipe* hp = nullptr,
+                double* out_abq = nullptr) {
   c->launch_count = 0;
   c->gadd_active = false;
+  pdl_break(c);                        // whatever precedes this forward on `st` is not one of its kernels
   std::vector<cudaEvent_t>* ev = nullptr;
   auto mark = [&]() {
     if (!ev) return;
@@ -499,6 +501,7 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
     else cudaEventCreate(&e);
     cudaEventRecord(e, st);
     ev->push_back(e);
+    pdl_break(c);                      // per-op timing: kernels must not overlap their predecessors
   };
   if (c->profiling) { c->prof_runs.emplace_back(); ev = &c->prof_runs.back(); }
   mark();
@@ -511,6 +514,7 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
   if (hp) {
     for (int k = 0; k < hp->nchunks; ++k) {
       CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_in[k], 0));
+      pdl_break(c);
       CUDA_TRY(c, launch_conv1_1(c, hp->start[k + 1] - hp->start[k], L, ab, mask, maskcent, st, hp->start[k]));
     }
   } else {
@@ -525,6 +529,7 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
         const int i0 = hp->start[k], nk = hp->start[k + 1] - i0;
         CUDA_TRY(c, umma_run_op(c, op, nk, out_ab, 1.0f, st, i0));
         CUDA_TRY(c, cudaEventRecord(c->ev_out[k], st));
+        pdl_break(c);
         CUDA_TRY(c, cudaStreamWaitEvent(c->s_out, c->ev_out[k], 0));
         CUDA_TRY(c, cudaMemcpyAsync(hp->ab_dst + (size_t)i0 * 2 * HW, out_ab + (size_t)i0 * 2 * HW,
                                     (size_t)nk * 2 * HW * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
@@ -538,10 +543,11 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
   if (!fused) CUDA_TRY(c, launch_out_head(c, n, out_ab, st));
   if (out_dist) CUDA_TRY(c, launch_softmax529(c, n, out_dist, st));
   if (out_rgb) {
-    CUDA_TRY(c, launch_lab2rgb(n, c->H, c->W, L, 50.0f, out_ab, out_rgb, st));
+    CUDA_TRY(c, launch_lab2rgb(c, n, c->H, c->W, L, 50.0f, out_ab, out_rgb, st, out_abq));
     c->launch_count++;
   }
   mark();
+  pdl_break(c);
   c->last_n = n;
   return IDC_OK;
 }
@@ -591,6 +597,27 @@ int idc_create(int device, int max_n, int h, int w, unsigned flags, idc_ctx** ou
   cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
   *out = c;
   return IDC_OK;
+}
+
+int idc_set_option(idc_ctx* c, const char* name, int value) {
+  if (!c || !name) return IDC_ERR_ARG;
+  struct { const char* n; int* v; } tab[] = {
+      {"halo", &c->opt.halo}, {"pairs", &c->opt.pairs}, {"mt", &c->opt.mt}, {"chunk_kb", &c->opt.chunk_kb},
+      {"split_k", &c->opt.split_k}, {"direct_stores", &c->opt.direct_stores}, {"host_pipe", &c->opt.host_pipe},
+      {"pdl", &c->opt.pdl}, {"split_pairs", &c->opt.split_pairs}};
+  for (auto& t : tab)
+    if (!strcmp(t.n, name)) {
+      *t.v = value;
+      if (c->weights_ready && strcmp(name, "host_pipe")) {      // plan-time option changed after planning: re-plan
+        CUDA_TRY(c, cudaSetDevice(c->dev));
+        CUDA_TRY(c, cudaDeviceSynchronize());
+        int rc = plan_engines(c);
+        if (rc != IDC_OK) return rc;
+      }
+      if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+      return IDC_OK;
+    }
+  return fail(c, IDC_ERR_KEY, "unknown option '%s'", name);
 }
 
 int idc_load_tensor(idc_ctx* c, const char* key, const void* data, int dtype, int ndim, const int64_t* dims) {
@@ -668,6 +695,10 @@ int idc_forward(idc_ctx* c, int n, int h, int w, const float* L, const float* ab
   int rc = check_forward_args(c, n, h, w, L, ab, mask, glob, out_ab, out_dist);
   if (rc != IDC_OK) return rc;
   CUDA_TRY(c, cudaSetDevice(c->dev));
+  if (int werr = *(volatile int*)c->h_err) {           // left by an earlier (asynchronous) forward
+    *(volatile int*)c->h_err = 0;
+    return fail(c, IDC_ERR_WATCHDOG, "device pipeline watchdog fired earlier (code %d)", werr);
+  }
   return run_forward(c, n, L, ab, mask, maskcent, glob, out_ab, out_dist, out_rgb, (cudaStream_t)stream);
 }
 
@@ -679,20 +710,117 @@ static bool is_pinned(const void* p) {
 
 int idc_forward_host(idc_ctx* c, int n, int h, int w, const float* L, const float* ab, const float* mask,
                      float maskcent, const float* glob, float* out_ab, float* out_dist, uint8_t* out_rgb) {
+  return idc_forward_host_q(c, n, h, w, L, ab, mask, maskcent, glob, out_ab, out_dist, out_rgb, nullptr);
+}
+
+// Small batches (the interactive click): ONE graph launch does everything -- a single H2D of the compact staging
+// block [L | ab | mask | glob], the kernels (chained by programmatic dependent launch), a single D2H of the compact
+// result block [ab | rgb | quantised ab].  Caller buffers are copied to / from the pinned staging blocks by the CPU.
+static int forward_host_small(idc_ctx* c, int n, const float* L, const float* ab, const float* mask, float maskcent,
+                              const float* glob, float* out_ab, float* out_dist, uint8_t* out_rgb, double* out_abq) {
+  const size_t HW = (size_t)c->H * c->W, HW4 = (size_t)(c->H / 4) * (c->W / 4);
+  cudaStream_t st = c->own_stream;
+  const bool copy_dist = out_dist != nullptr;
+  const bool want_dist = copy_dist || (c->dist_resident && c->dist);
+  const bool want_rgb = out_rgb != nullptr, want_glob = glob != nullptr, want_q = out_abq != nullptr;
+  // compact device / host layouts for this n
+  float* dL = c->d_in; float* dab = dL + (size_t)n * HW; float* dmask = dab + (size_t)n * 2 * HW;
+  float* dglob = dmask + (size_t)n * HW;
+  const size_t in_floats = (size_t)n * 4 * HW + (want_glob ? (size_t)n * 316 : 0);
+  const size_t b_ab = (size_t)n * 2 * HW * sizeof(float), b_rgb = (size_t)n * 3 * HW, b_q = (size_t)n * 2 * HW * sizeof(double);
+  char* dsm = c->d_small; char* hsm = c->h_small;
+  float* dout = reinterpret_cast<float*>(dsm);
+  uint8_t* drgb = reinterpret_cast<uint8_t*>(dsm + b_ab);
+  double* dq = reinterpret_cast<double*>(dsm + b_ab + b_rgb);
+  float* ddist = c->d_out + (size_t)c->max_n * 2 * HW;
+  const size_t out_bytes = b_ab + (want_rgb ? b_rgb : 0) + (want_q ? b_q : 0);
+  // stage the inputs
+  memcpy(c->h_in, L, (size_t)n * HW * sizeof(float));
+  memcpy(c->h_in + (size_t)n * HW, ab, (size_t)n * 2 * HW * sizeof(float));
+  memcpy(c->h_in + (size_t)n * 3 * HW, mask, (size_t)n * HW * sizeof(float));
+  if (want_glob) memcpy(c->h_in + (size_t)n * 4 * HW, glob, (size_t)n * 316 * sizeof(float));
+
+  const void* key[8] = {(void*)(size_t)n, (void*)(size_t)want_dist, (void*)(size_t)want_rgb, (void*)(size_t)want_glob,
+                        (void*)(size_t)want_q, (void*)(size_t)copy_dist, nullptr, nullptr};
+  if (!c->graph_exec || memcmp(key, c->graph_ptrs, sizeof(key)) != 0 || c->graph_maskcent != maskcent) {
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    cudaGraph_t g = nullptr;
+    CUDA_TRY(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const bool prof = c->profiling;
+    c->profiling = false;            // event timing is meaningless inside a capture
+    cudaError_t ce = cudaMemcpyAsync(c->d_in, c->h_in, in_floats * sizeof(float), cudaMemcpyHostToDevice, st);
+    int rc = IDC_OK;
+    if (ce == cudaSuccess)
+      rc = run_forward(c, n, dL, dab, dmask, maskcent, want_glob ? dglob : nullptr, dout, want_dist ? ddist : nullptr,
+                       want_rgb ? drgb : nullptr, st, nullptr, want_q ? dq : nullptr);
+    if (ce == cudaSuccess && rc == IDC_OK) ce = cudaMemcpyAsync(hsm, dsm, out_bytes, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess && rc == IDC_OK && copy_dist)
+      ce = cudaMemcpyAsync(c->h_out + (size_t)c->max_n * 2 * HW, ddist, (size_t)n * 529 * HW4 * sizeof(float),
+                           cudaMemcpyDeviceToHost, st);
+    c->profiling = prof;
+    cudaError_t ce2 = cudaStreamEndCapture(st, &g);
+    if (rc != IDC_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (ce != cudaSuccess) { if (g) cudaGraphDestroy(g); CUDA_TRY(c, ce); }
+    CUDA_TRY(c, ce2);
+    ce = cudaGraphInstantiate(&c->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    CUDA_TRY(c, ce);
+    memcpy(c->graph_ptrs, key, sizeof(key));
+    c->graph_maskcent = maskcent;
+    c->graph_launches = c->launch_count;
+  }
+  CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, st));
+  c->launch_count = c->graph_launches;
+  c->last_n = n;
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  memcpy(out_ab, hsm, b_ab);
+  if (want_rgb) memcpy(out_rgb, hsm + b_ab, b_rgb);
+  if (want_q) memcpy(out_abq, hsm + b_ab + b_rgb, b_q);
+  if (copy_dist) memcpy(out_dist, c->h_out + (size_t)c->max_n * 2 * HW, (size_t)n * 529 * HW4 * sizeof(float));
+  c->dist_valid_n = want_dist ? n : 0;
+  return IDC_OK;
+}
+
+int idc_forward_host_q(idc_ctx* c, int n, int h, int w, const float* L, const float* ab, const float* mask,
+                       float maskcent, const float* glob, float* out_ab, float* out_dist, uint8_t* out_rgb,
+                       double* out_abq) {
   if (!c) return IDC_ERR_ARG;
   int rc = check_forward_args(c, n, h, w, L, ab, mask, glob, out_ab, out_dist);
   if (rc != IDC_OK) return rc;
+  if (out_abq && !out_rgb) return fail(c, IDC_ERR_ARG, "out_abq (quantised ab) is derived from out_rgb: pass both");
   CUDA_TRY(c, cudaSetDevice(c->dev));
+  if (int werr = *(volatile int*)c->h_err) {           // a watchdog left over from an asynchronous idc_forward
+    *(volatile int*)c->h_err = 0;
+    return fail(c, IDC_ERR_WATCHDOG, "device pipeline watchdog fired earlier (code %d)", werr);
+  }
   const size_t HW = (size_t)c->H * c->W, HW4 = (size_t)(c->H / 4) * (c->W / 4);
+  const int small_n = c->max_n < 4 ? c->max_n : 4;
   if (!c->d_in) {
     c->in_floats = (size_t)c->max_n * (4 * HW + 316);
     c->out_floats = (size_t)c->max_n * (2 * HW + (c->dist ? 529 * HW4 : 0));
+    const size_t small_bytes = (size_t)small_n * (2 * HW * 4 + 3 * HW + 2 * HW * 8);
     CUDA_TRY(c, cudaMalloc(&c->d_in, c->in_floats * sizeof(float)));
     CUDA_TRY(c, cudaMalloc(&c->d_out, c->out_floats * sizeof(float)));
     CUDA_TRY(c, cudaMalloc(&c->d_rgb, (size_t)c->max_n * HW * 3));
+    CUDA_TRY(c, cudaMalloc(&c->d_small, small_bytes));
     CUDA_TRY(c, cudaMallocHost(&c->h_in, c->in_floats * sizeof(float)));
     CUDA_TRY(c, cudaMallocHost(&c->h_out, c->out_floats * sizeof(float)));
     CUDA_TRY(c, cudaMallocHost(&c->h_rgb, (size_t)c->max_n * HW * 3));
+    CUDA_TRY(c, cudaMallocHost(&c->h_small, small_bytes));
+  }
+  const bool use_graph = !(c->flags & IDC_FLAG_NO_GRAPH) && n <= 4;
+  if (use_graph) {
+    rc = forward_host_small(c, n, L, ab, mask, maskcent, glob, out_ab, out_dist, out_rgb, out_abq);
+    if (rc != IDC_OK) return rc;
+    if (int werr = *(volatile int*)c->h_err) {
+      *(volatile int*)c->h_err = 0;
+      return fail(c, IDC_ERR_WATCHDOG, "device pipeline watchdog fired (code %d)", werr);
+    }
+    return IDC_OK;
+  }
+  if (out_abq && !c->d_abq) {
+    CUDA_TRY(c, cudaMalloc(&c->d_abq, (size_t)c->max_n * 2 * HW * sizeof(double)));
+    CUDA_TRY(c, cudaMallocHost(&c->h_abq, (size_t)c->max_n * 2 * HW * sizeof(double)));
   }
   cudaStream_t st = c->own_stream;
   // device-side layout of the staging block: [L | ab | mask | glob], [out_ab | out_dist]
@@ -707,14 +835,13 @@ int idc_forward_host(idc_ctx* c, int n, int h, int w, const float* L, const floa
     }
     return cudaMemcpyAsync(d, s, count * sizeof(float), cudaMemcpyHostToDevice, st);
   };
-  const bool use_graph = !(c->flags & IDC_FLAG_NO_GRAPH) && n <= 4;
-  // large batches: chunked copy/compute overlap (see HostPipe); IDC_HOST_PIPE=0 turns it off for A/B runs
-  static const bool pipe_env = !(getenv("IDC_HOST_PIPE") && atoi(getenv("IDC_HOST_PIPE")) == 0);
+  // large batches: chunked copy/compute overlap (see HostPipe); option host_pipe=0 turns it off for A/B runs
+  const bool pipe_on = c->opt.host_pipe != 0;
   const bool fused_head = !c->simt && !(c->flags & IDC_FLAG_KEEP_CONV10);
   HostPipe hp;
   bool last_splits = false;
   for (auto& op : c->ops) if (op.fuse_out_head) last_splits = umma_op_uses_split_k(op);
-  if (pipe_env && !use_graph && n >= 8 && fused_head && !last_splits && !c->profiling) {
+  if (pipe_on && n >= 8 && fused_head && !last_splits && !c->profiling) {
     hp.nchunks = n >= 32 ? 4 : 2;   // measured: 8 chunks at n = 64 is 1.3 % slower end to end than 4
     for (int k = 0; k <= hp.nchunks; ++k) hp.start[k] = (int)((long long)n * k / hp.nchunks);
     hp.ab_dst = is_pinned(out_ab) ? out_ab : c->h_out;
@@ -749,34 +876,9 @@ int idc_forward_host(idc_ctx* c, int n, int h, int w, const float* L, const floa
   const bool copy_dist = out_dist != nullptr;
   const bool want_dist = copy_dist || (c->dist_resident && c->dist);
   const bool want_rgb = out_rgb != nullptr, want_glob = glob != nullptr;
-  if (use_graph) {
-    const void* key[8] = {(void*)(size_t)n, (void*)(size_t)want_dist, (void*)(size_t)want_rgb, (void*)(size_t)want_glob,
-                          nullptr, nullptr, nullptr, nullptr};
-    if (!c->graph_exec || memcmp(key, c->graph_ptrs, sizeof(key)) != 0 || c->graph_maskcent != maskcent) {
-      if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
-      cudaGraph_t g = nullptr;
-      CUDA_TRY(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      const bool prof = c->profiling;
-      c->profiling = false;            // event timing is meaningless inside a capture
-      rc = run_forward(c, n, dL, dab, dmask, maskcent, want_glob ? dglob : nullptr, dout, want_dist ? ddist : nullptr,
-                       want_rgb ? c->d_rgb : nullptr, st);
-      c->profiling = prof;
-      cudaError_t ce = cudaStreamEndCapture(st, &g);
-      if (rc != IDC_OK) { if (g) cudaGraphDestroy(g); return rc; }
-      CUDA_TRY(c, ce);
-      CUDA_TRY(c, cudaGraphInstantiate(&c->graph_exec, g, 0));
-      cudaGraphDestroy(g);
-      memcpy(c->graph_ptrs, key, sizeof(key));
-      c->graph_maskcent = maskcent;
-      c->graph_launches = c->launch_count;
-    }
-    CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, st));
-    c->launch_count = c->graph_launches;
-  } else {
-    rc = run_forward(c, n, dL, dab, dmask, maskcent, want_glob ? dglob : nullptr, dout, want_dist ? ddist : nullptr,
-                     want_rgb ? c->d_rgb : nullptr, st, hp.nchunks ? &hp : nullptr);
-    if (rc != IDC_OK) return rc;
-  }
+  rc = run_forward(c, n, dL, dab, dmask, maskcent, want_glob ? dglob : nullptr, dout, want_dist ? ddist : nullptr,
+                   want_rgb ? c->d_rgb : nullptr, st, hp.nchunks ? &hp : nullptr, out_abq ? c->d_abq : nullptr);
+  if (rc != IDC_OK) return rc;
   auto d2h = [&](void* dst, const void* d, size_t bytes, void* stage) -> cudaError_t {
     if (is_pinned(dst)) return cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, st);
     return cudaMemcpyAsync(stage, d, bytes, cudaMemcpyDeviceToHost, st);
@@ -784,14 +886,18 @@ int idc_forward_host(idc_ctx* c, int n, int h, int w, const float* L, const floa
   if (!hp.nchunks) CUDA_TRY(c, d2h(out_ab, dout, n * 2 * HW * sizeof(float), c->h_out));
   if (copy_dist) CUDA_TRY(c, d2h(out_dist, ddist, n * 529 * HW4 * sizeof(float), c->h_out + (size_t)c->max_n * 2 * HW));
   if (want_rgb) CUDA_TRY(c, d2h(out_rgb, c->d_rgb, n * HW * 3, c->h_rgb));
+  if (out_abq) CUDA_TRY(c, d2h(out_abq, c->d_abq, n * 2 * HW * sizeof(double), c->h_abq));
   CUDA_TRY(c, cudaStreamSynchronize(st));
   if (hp.nchunks) CUDA_TRY(c, cudaStreamSynchronize(c->s_out));
   if (!is_pinned(out_ab)) memcpy(out_ab, c->h_out, n * 2 * HW * sizeof(float));
   if (copy_dist && !is_pinned(out_dist)) memcpy(out_dist, c->h_out + (size_t)c->max_n * 2 * HW, n * 529 * HW4 * sizeof(float));
   c->dist_valid_n = want_dist ? n : 0;
   if (want_rgb && !is_pinned(out_rgb)) memcpy(out_rgb, c->h_rgb, n * HW * 3);
-  const int werr = *(volatile int*)c->h_err;
-  if (werr) return fail(c, IDC_ERR_WATCHDOG, "device pipeline watchdog fired (code %d)", werr);
+  if (out_abq && !is_pinned(out_abq)) memcpy(out_abq, c->h_abq, n * 2 * HW * sizeof(double));
+  if (int werr = *(volatile int*)c->h_err) {
+    *(volatile int*)c->h_err = 0;
+    return fail(c, IDC_ERR_WATCHDOG, "device pipeline watchdog fired (code %d)", werr);
+  }
   return IDC_OK;
 }
 
@@ -912,7 +1018,7 @@ int idc_caffe313_dist_pixel(idc_ctx* c, int img, int y, int x, float S, float* o
 int idc_lab2rgb_u8(int device, int n, int h, int w, const float* L, const float* ab, uint8_t* rgb, void* stream) {
   if (n < 1 || h < 1 || w < 1 || !L || !ab || !rgb) return IDC_ERR_ARG;
   if (cudaSetDevice(device) != cudaSuccess) return IDC_ERR_CUDA;
-  return launch_lab2rgb(n, h, w, L, 0.0f, ab, rgb, (cudaStream_t)stream) == cudaSuccess ? IDC_OK : IDC_ERR_CUDA;
+  return launch_lab2rgb(nullptr, n, h, w, L, 0.0f, ab, rgb, (cudaStream_t)stream) == cudaSuccess ? IDC_OK : IDC_ERR_CUDA;
 }
 
 int idc_global_stats(int device, int h, int w, const uint8_t* rgb, const float* pts313, float* out316, void* stream) {
@@ -990,6 +1096,10 @@ int idc_get_profile(idc_ctx* c, float* ms, int max_slots) {
   if (max_slots < slots) return fail(c, IDC_ERR_ARG, "need %d slots", slots);
   CUDA_TRY(c, cudaSetDevice(c->dev));
   CUDA_TRY(c, cudaDeviceSynchronize());
+  if (int werr = *(volatile int*)c->h_err) {
+    *(volatile int*)c->h_err = 0;
+    return fail(c, IDC_ERR_WATCHDOG, "device pipeline watchdog fired (code %d)", werr);
+  }
   for (int i = 0; i < slots; ++i) ms[i] = 0.f;
   int runs = 0;
   for (auto& ev : c->prof_runs) {
@@ -1065,6 +1175,10 @@ int idc_destroy(idc_ctx* c) {
   if (c->d_in) cudaFree(c->d_in);
   if (c->d_out) cudaFree(c->d_out);
   if (c->d_rgb) cudaFree(c->d_rgb);
+  if (c->d_small) cudaFree(c->d_small);
+  if (c->h_small) cudaFreeHost(c->h_small);
+  if (c->d_abq) cudaFree(c->d_abq);
+  if (c->h_abq) cudaFreeHost(c->h_abq);
   if (c->h_in) cudaFreeHost(c->h_in);
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_rgb) cudaFreeHost(c->h_rgb);

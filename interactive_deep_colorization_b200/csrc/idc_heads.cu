@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(128) conv1_1_kernel(const __grid_constant__ Co
                                                       const float* __restrict__ mask, float maskcent, int N, int H,
                                                       int Wd, float* __restrict__ outf, __half* __restrict__ ohi,
                                                       __half* __restrict__ olo) {
+  pdl_prologue_done();
   const size_t HW = (size_t)H * Wd;
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = pix < (size_t)N * HW;                   // N*HW is a multiple of 64, blocks are 128 wide
@@ -116,14 +117,16 @@ cudaError_t launch_conv1_1(Ctx* c, int n, const float* L, const float* ab, const
   const size_t HW = (size_t)o.H * o.W, npix = (size_t)n * HW, ooff = (size_t)img0 * HW * o.C;
   const int grid = (int)((npix + 127) / 128);
   L += img0 * HW; ab += img0 * 2 * HW; mask += img0 * HW;
+  cudaError_t e;
   if (c->simt)
-    conv1_1_kernel<false><<<grid, 128, 0, st>>>(c->h_w11, L, ab, mask, maskcent, n, o.H, o.W,
-                                                static_cast<float*>(o.p0) + ooff, nullptr, nullptr);
+    e = launch_k(c, conv1_1_kernel<false>, dim3(grid), dim3(128), 0, st, c->h_w11, L, ab, mask, maskcent, n, o.H, o.W,
+                 static_cast<float*>(o.p0) + ooff, (__half*)nullptr, (__half*)nullptr);
   else
-    conv1_1_kernel<true><<<grid, 128, 0, st>>>(c->h_w11, L, ab, mask, maskcent, n, o.H, o.W, nullptr,
-                                               static_cast<__half*>(o.p0) + ooff, static_cast<__half*>(o.p1) + ooff);
+    e = launch_k(c, conv1_1_kernel<true>, dim3(grid), dim3(128), 0, st, c->h_w11, L, ab, mask, maskcent, n, o.H, o.W,
+                 (float*)nullptr, static_cast<__half*>(o.p0) + ooff,
+                 o.p1 ? static_cast<__half*>(o.p1) + ooff : (__half*)nullptr);   // FAST_FP16: no lo plane
   c->launch_count++;
-  return cudaGetLastError();
+  return e;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -135,7 +138,8 @@ __global__ void __launch_bounds__(256) out_head_kernel(const float* __restrict__
                                                        const float* __restrict__ b, int N, int H, int W,
                                                        float* __restrict__ out) {
   __shared__ float ws[256];
-  ws[threadIdx.x] = w[threadIdx.x];
+  ws[threadIdx.x] = w[threadIdx.x];                     // static weights: before the dependency wait
+  pdl_prologue_done();
   __syncthreads();
   const size_t HW = (size_t)H * W;
   const size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
@@ -170,15 +174,16 @@ cudaError_t launch_out_head(Ctx* c, int n, float* out_ab, cudaStream_t st) {
   const ActBuf& in = c->bufs[c->buf_index.at("conv10_2")];
   const size_t npix = (size_t)n * in.H * in.W;
   const int grid = (int)((npix * 8 + 255) / 256);
+  cudaError_t e;
   if (c->simt)
-    out_head_kernel<false><<<grid, 256, 0, st>>>(static_cast<const float*>(in.p0), nullptr, nullptr, c->wout, c->bout,
-                                                 n, in.H, in.W, out_ab);
+    e = launch_k(c, out_head_kernel<false>, dim3(grid), dim3(256), 0, st, static_cast<const float*>(in.p0),
+                 (const __half*)nullptr, (const __half*)nullptr, c->wout, c->bout, n, in.H, in.W, out_ab);
   else
-    out_head_kernel<true><<<grid, 256, 0, st>>>(nullptr, static_cast<const __half*>(in.p0),
-                                                static_cast<const __half*>(in.p1), c->wout, c->bout, n, in.H, in.W,
-                                                out_ab);
+    e = launch_k(c, out_head_kernel<true>, dim3(grid), dim3(256), 0, st, (const float*)nullptr,
+                 static_cast<const __half*>(in.p0), static_cast<const __half*>(in.p1), c->wout, c->bout, n, in.H, in.W,
+                 out_ab);
   c->launch_count++;
-  return cudaGetLastError();
+  return e;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -189,6 +194,7 @@ constexpr int kBins = 529;
 __global__ void __launch_bounds__(256) softmax529_kernel(const float* __restrict__ logits, int ld, int M, int HW4,
                                                          float* __restrict__ out) {
   extern __shared__ float tile[];  // [529][33]
+  pdl_prologue_done();
   const int p0 = blockIdx.x * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int q = 0; q < 4; ++q) {
@@ -239,14 +245,15 @@ cudaError_t launch_softmax529(Ctx* c, int n, float* out_dist, cudaStream_t st) {
   for (auto& op : c->ops)
     if (op.kind == OP_CLASS) ld = op.cout_pad;
   const size_t smem = (size_t)kBins * 33 * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(softmax529_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
+  static unsigned long long attr_devs = 0;       // the opt-in is per device: one bit per device ordinal
+  if (c->dev >= 64 || !(attr_devs & (1ull << c->dev))) {
+    cudaError_t e = cudaFuncSetAttribute(softmax529_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (c->dev < 64) attr_devs |= 1ull << c->dev;
   }
-  softmax529_kernel<<<ceil_div(M, 32), 256, smem, st>>>(c->logits, ld, M, HW4, out_dist);
+  cudaError_t e = launch_k(c, softmax529_kernel, dim3(ceil_div(M, 32)), dim3(256), smem, st, c->logits, ld, M, HW4, out_dist);
   c->launch_count++;
-  return cudaGetLastError();
+  return e;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -254,14 +261,22 @@ cudaError_t launch_softmax529(Ctx* c, int n, float* out_dist, cudaStream_t st) {
 // skimage 0.13 color.lab2rgb (lab2xyz + xyz2rgb), clip, *255, truncating cast
 // (data/colorize_image.py:27).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double srgb_inv_gamma(double c) {
+  return c > 0.04045 ? pow((c + 0.055) / 1.055, 2.4) : c / 12.92;
+}
+__device__ __forceinline__ double lab_f(double t) { return t > 0.008856 ? cbrt(t) : 7.787 * t + 16.0 / 116.0; }
+
 __device__ __forceinline__ double lab_finv(double t) {
   return t > 0.2068966 ? t * t * t : (t - 16.0 / 116.0) / 7.787;
 }
 __device__ __forceinline__ double srgb_gamma(double c) {
   return c > 0.0031308 ? 1.055 * pow(c, 1.0 / 2.4) - 0.055 : 12.92 * c;
 }
+// abq (optional): the reference's quantised `output_ab` = rgb2lab(uint8 RGB)[1:] (data/colorize_image.py:196-198,
+// row a11) computed from the just-quantised pixel in the same thread, [N,2,HW] float64.
 __global__ void lab2rgb_kernel(const float* __restrict__ L, float l_offset, const float* __restrict__ ab, int N,
-                               int HW, uint8_t* __restrict__ rgb) {
+                               int HW, uint8_t* __restrict__ rgb, double* __restrict__ abq) {
+  pdl_prologue_done();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)N * HW) return;
   const int n = (int)(i / HW);
@@ -285,9 +300,18 @@ __global__ void lab2rgb_kernel(const float* __restrict__ L, float l_offset, cons
   R = fmin(fmax(R, 0.0), 1.0) * 255.0;
   G = fmin(fmax(G, 0.0), 1.0) * 255.0;
   B = fmin(fmax(B, 0.0), 1.0) * 255.0;
-  rgb[i * 3 + 0] = (uint8_t)R;
-  rgb[i * 3 + 1] = (uint8_t)G;
-  rgb[i * 3 + 2] = (uint8_t)B;
+  const uint8_t r8 = (uint8_t)R, g8 = (uint8_t)G, b8 = (uint8_t)B;
+  rgb[i * 3 + 0] = r8;
+  rgb[i * 3 + 1] = g8;
+  rgb[i * 3 + 2] = b8;
+  if (abq) {   // same arithmetic as rgb2lab_kernel below
+    const double rl = srgb_inv_gamma(r8 / 255.0), gl = srgb_inv_gamma(g8 / 255.0), bl = srgb_inv_gamma(b8 / 255.0);
+    const double fx2 = lab_f((0.412453 * rl + 0.357580 * gl + 0.180423 * bl) / 0.95047);
+    const double fy2 = lab_f((0.212671 * rl + 0.715160 * gl + 0.072169 * bl) / 1.0);
+    const double fz2 = lab_f((0.019334 * rl + 0.119193 * gl + 0.950227 * bl) / 1.08883);
+    abq[(size_t)n * 2 * HW + r] = 500.0 * (fx2 - fy2);
+    abq[(size_t)n * 2 * HW + HW + r] = 200.0 * (fy2 - fz2);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -296,11 +320,6 @@ __global__ void lab2rgb_kernel(const float* __restrict__ L, float l_offset, cons
 //   zoom_lab2rgb_kernel  scipy.ndimage.zoom(order=1) of the ab planes to the full-resolution grid +
 //                        lab2rgb_transpose with the full-resolution L (get_img_fullres, :123-131)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double srgb_inv_gamma(double c) {
-  return c > 0.04045 ? pow((c + 0.055) / 1.055, 2.4) : c / 12.92;
-}
-__device__ __forceinline__ double lab_f(double t) { return t > 0.008856 ? cbrt(t) : 7.787 * t + 16.0 / 116.0; }
-
 __global__ void rgb2lab_kernel(const uint8_t* __restrict__ rgb, int N, int HW, double* __restrict__ lab) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)N * HW) return;
@@ -440,11 +459,10 @@ cudaError_t launch_zoom_lab2rgb(const double* ab, int hin, int win, const double
   return cudaGetLastError();
 }
 
-cudaError_t launch_lab2rgb(int n, int h, int w, const float* L, float l_offset, const float* ab, uint8_t* rgb,
-                           cudaStream_t st) {
+cudaError_t launch_lab2rgb(Ctx* c, int n, int h, int w, const float* L, float l_offset, const float* ab, uint8_t* rgb,
+                           cudaStream_t st, double* abq) {
   const size_t tot = (size_t)n * h * w;
-  lab2rgb_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(L, l_offset, ab, n, h * w, rgb);
-  return cudaGetLastError();
+  return launch_k(c, lab2rgb_kernel, dim3((unsigned)((tot + 127) / 128)), dim3(128), 0, st, L, l_offset, ab, n, h * w, rgb, abq);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -574,6 +592,7 @@ cudaError_t launch_dist313_pixel(Ctx* c, int img, int y, int x, float S, float* 
 __global__ void dense_relu_bn_kernel(const float* __restrict__ x, int xin, int xld, const float* __restrict__ w,
                                      const float* __restrict__ b, const float* __restrict__ scale,
                                      const float* __restrict__ shift, int cout, float* __restrict__ y, int yld) {
+  pdl_prologue_done();
   const int n = blockIdx.y;
   const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -595,8 +614,9 @@ cudaError_t launch_global_mlp(Ctx* c, int n, const float* glob, cudaStream_t st)
   for (int l = 0; l < 4; ++l) {
     float* y = (l == 3) ? c->gvec : c->gtmp + (size_t)(l & 1) * c->max_n * 512;
     dim3 grid(512 / 8, n);
-    dense_relu_bn_kernel<<<grid, 256, 0, st>>>(x, xin, xld, c->gw[l], c->gb[l], c->gscale[l], c->gshift[l], 512, y,
-                                               512);
+    cudaError_t e = launch_k(c, dense_relu_bn_kernel, grid, dim3(256), 0, st, x, xin, xld, (const float*)c->gw[l],
+                             (const float*)c->gb[l], (const float*)c->gscale[l], (const float*)c->gshift[l], 512, y, 512);
+    if (e != cudaSuccess) return e;
     c->launch_count++;
     x = y; xin = 512; xld = 512;
   }

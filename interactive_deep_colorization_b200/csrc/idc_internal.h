@@ -106,6 +106,20 @@ struct Conv11Weights {
   float b[64];
 };
 
+// Plan-time options (idc_set_option).  -1 = automatic.  They replace the IDC_* environment switches of
+// round 1: a C ABI that is embedded in someone else's process must not read process-global state.
+struct Options {
+  int halo = 1;           // halo-tile A operand: 0 off, 1 = 128-column stride-1 3x3 layers that fill the machine, 3 = every eligible op
+  int pairs = 1;          // cta_group::2: 0 never, 1 = launches that give every SM pair >= 2 tiles, 2 = always
+  int mt = -1;            // M-tiles per CTA tile on the <= 128-column layers (1 / 2)
+  int chunk_kb = -1;      // k-blocks summed in TMEM before the FP32 round-to-nearest add
+  int split_k = -1;       // K slices per tile on launches that cannot fill the machine
+  int direct_stores = 0;  // 1 = per-lane 16-byte stores instead of the warp-transposed ones
+  int host_pipe = 1;      // idc_forward_host: chunked copy/compute overlap for batches >= 8
+  int pdl = 1;            // programmatic dependent launch between the kernels of a forward
+  int split_pairs = 1;    // cta_group::2 on the split-K (small batch) path
+};
+
 struct HostTensor {
   std::vector<float> data;
   std::vector<int64_t> dims;
@@ -115,6 +129,7 @@ struct Ctx {
   int dev = 0;
   int max_n = 0, H = 0, W = 0;
   unsigned flags = 0;
+  Options opt;
   bool simt = false, fast = false, dist = false, glob = false;
   std::map<std::string, HostTensor> raw;
   std::vector<ActBuf> bufs;
@@ -152,6 +167,8 @@ struct Ctx {
   float* h_in = nullptr;  float* d_in = nullptr;   size_t in_floats = 0;
   float* h_out = nullptr; float* d_out = nullptr;  size_t out_floats = 0;
   uint8_t* h_rgb = nullptr; uint8_t* d_rgb = nullptr;
+  char* h_small = nullptr; char* d_small = nullptr;   // compact [ab | rgb | quantised ab] block of the batch <= 4 graph path
+  double* h_abq = nullptr; double* d_abq = nullptr;   // quantised ab (row a11) of the large-batch path
   cudaStream_t own_stream = nullptr;
   // idc_forward_host pipeline (large batches): H2D of image chunk k+1 overlaps conv1_1 of chunk k, D2H of ab
   // chunk k overlaps the last op of chunk k+1
@@ -163,6 +180,7 @@ struct Ctx {
   float graph_maskcent = 0.f;
   int launch_count = 0;
   int graph_launches = 0;
+  bool chain = false;           // the previous operation on the forward's stream was a kernel of this forward (PDL)
   bool gadd_active = false;     // a global-hints vector was supplied to this forward
   int last_n = 0;
   double* d_reccs = nullptr;    // idc_ab_reccs scratch (results of every restart, then the 529x2 gamut points)
@@ -186,8 +204,8 @@ cudaError_t launch_conv1_1(Ctx* c, int n, const float* L, const float* ab, const
                            float maskcent, cudaStream_t st, int img0 = 0);   // L/ab/mask: full arrays; images img0..img0+n
 cudaError_t launch_out_head(Ctx* c, int n, float* out_ab, cudaStream_t st);   // SIMT / KEEP_CONV10 path
 cudaError_t launch_softmax529(Ctx* c, int n, float* out_dist, cudaStream_t st);
-cudaError_t launch_lab2rgb(int n, int h, int w, const float* L, float l_offset, const float* ab,
-                           uint8_t* rgb, cudaStream_t st);
+cudaError_t launch_lab2rgb(Ctx* c, int n, int h, int w, const float* L, float l_offset, const float* ab,
+                           uint8_t* rgb, cudaStream_t st, double* abq = nullptr);   // c may be null (stand-alone call)
 cudaError_t launch_decode313(Ctx* c, int n, float T, float* out_ab, cudaStream_t st);
 cudaError_t launch_dist313_pixel(Ctx* c, int img, int y, int x, float S, float* out313_dev, cudaStream_t st);
 cudaError_t launch_ab_reccs(const float* pmf, size_t bin_stride, const float* pts_dev, int K, int max_iter,
@@ -201,5 +219,34 @@ cudaError_t launch_act_to_nchw(Ctx* c, const ActBuf& b, int n, float* out, cudaS
 cudaError_t launch_nchw_to_act(Ctx* c, const ActBuf& b, int n, const float* in, cudaStream_t st);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Programmatic dependent launch bookkeeping: a kernel may carry the programmatic-stream-serialization attribute
+// only when the operation enqueued right before it on the same stream is another kernel of this forward (every
+// kernel of the library executes griddepcontrol.wait, so completion stays transitive along the chain).
+inline bool pdl_take(Ctx* c) {
+  const bool r = c && c->opt.pdl && !c->simt && c->chain;
+  if (c) c->chain = true;
+  return r;
+}
+inline void pdl_break(Ctx* c) { if (c) c->chain = false; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_prologue_done() {   // small kernels: let the successor start, then wait for the predecessor
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(Ctx* c, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_take(c) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 }  // namespace idc

@@ -68,6 +68,7 @@ struct UmmaParams {
   float out_mult;
   int* err;
   long long* dbgbuf;   // experiments only: per-CTA cycle counters [grid][8]
+  int n_amaps;         // entries of `amaps` (prefetched in the prologue)
   int halo_groups;     // HALO kernels: 64-channel input groups (K = 9 taps x halo_groups k-blocks); kblk = {-, B k-column, dy+1, dx+1}
   int img0;            // first image of this launch (n_img = img0 + images of the launch): idc_forward_host
                        // runs the last op in image chunks so that the D2H of a chunk overlaps the next one
@@ -140,10 +141,28 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
       : "memory");
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor is still running; everything that depends on the predecessor's output sits behind
+// pdl_wait().  Every thread of every kernel of a forward executes pdl_wait() before it exits, so "kernel k is
+// complete" implies "kernels 0..k-1 are complete" (completion stays transitive along the chain).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// Read-only epilogue vectors: NOT volatile, so ptxas/nvcc may batch the loads of a slab ahead of its math (the
+// accumulate warps run 2 per scheduler and cannot hide a serialised ld.shared -> FFMA chain).  `addr` must be
+// derived from an epi_token() issued after the staging barrier, which pins the loads below that barrier.
 __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ uint32_t epi_token(uint32_t addr) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(addr) : "memory");
+  return r;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -342,6 +361,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
   }
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
+  if (threadIdx.x == 32) {                          // descriptors are input-independent: fetch them during the prologue
+    prefetch_tmap(&bmap_hi);
+    if (SPLIT) prefetch_tmap(&bmap_lo);
+    for (int i = 0; i < p.n_amaps; ++i) prefetch_tmap(p.amaps + i);
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), CG);        // pairs: both producers arrive on the leader's barrier
@@ -376,6 +400,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
   if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  pdl_launch_dependents();                           // the next kernel of the forward may start its own prologue
+  if (warp != 0) pdl_wait();                         // warp 0 first requests its weight tiles (see the producer)
 
   const int tiles_per_img = p.tiles_y * p.tiles_x;
   const int G = p.chunk_kb;
@@ -389,9 +415,44 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       uint32_t hcount = 0;                               // HALO: halo loads issued (slot = hcount & 1)
-      for (int w = blockIdx.x / CG; w < p.total_tiles * S; w += gridDim.x / CG) {
+      // Weights never depend on the previous layer: request the weight tiles of this CTA's first k-blocks BEFORE
+      // pdl_wait(), so they stream in while the predecessor kernel drains.  The stage's `full` barrier is armed
+      // with the byte count of the whole stage; the activation boxes follow after the wait.
+      const int w0 = blockIdx.x / CG;
+      int npre = 0;
+      if (w0 < p.total_tiles * S) {
+        const int tile = w0 / S, ks = w0 - tile * S;
+        const int kbeg = (ks * p.nkb) / S, kend = ((ks + 1) * p.nkb) / S;
+        int r = tile;
+        const int nt = r % p.n_tiles_n;
+        r /= p.n_tiles_n;
+        const int cls = r % p.ncls;
+        const int brow = cls * p.cout_pad + nt * BN + (int)cta_rank * (BN / CG);
+        const int4* kb = p.kblk + cls * p.nkb;
+        npre = kend - kbeg < STAGES ? kend - kbeg : STAGES;
+        if (elect_one()) {
+          for (int i = 0; i < npre; ++i) {
+            const uint32_t fb = smem_u32(&full_bar[i]);
+            const uint32_t sb = smem_u32(smem + i * SP::kStageBytes) + (SPLIT ? 2 : 1) * SP::kAStage;
+            const int kcol = HALO ? __ldg(kb + kbeg + i).y : (kbeg + i) * kBK;
+            if (PAIR) {
+              if (leader) mbar_expect_tx(fb, 2 * SP::kStageBytes); else mbar_arrive_rank0(fb);
+              tma_load_2d_pair(sb, &bmap_hi, fb, kcol, brow);
+              if (SPLIT) tma_load_2d_pair(sb + SP::kBBytes, &bmap_lo, fb, kcol, brow);
+            } else {
+              mbar_expect_tx(fb, SP::kStageBytes);
+              tma_load_2d(sb, &bmap_hi, fb, kcol, brow);
+              if (SPLIT) tma_load_2d(sb + SP::kBBytes, &bmap_lo, fb, kcol, brow);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      pdl_wait();                                        // activations of the previous layer are complete and visible
+      for (int w = w0; w < p.total_tiles * S; w += gridDim.x / CG) {
         const int tile = w / S, ks = w - tile * S;
         const int kbeg = (ks * p.nkb) / S, kend = ((ks + 1) * p.nkb) / S;
+        const int kpre = (w == w0) ? kbeg + npre : kbeg;        // k-blocks below kpre already have their weight tile
         // tile order: n-tile fastest, then output-parity class, then spatial tile, then image -- CTAs that
         // run together share the A tile (all n-tiles) and the source rows (all 4 classes of an up-layer).
         // Pairs: `tile` counts M-tile PAIRS; this CTA takes M-tile 2*pair + rank.
@@ -432,7 +493,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
               __syncwarp();
             }
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 1);
-            if (elect_one()) {
+            if (k >= kpre && elect_one()) {
               const uint32_t fb = smem_u32(&full_bar[stage]);
               const int4 e = __ldg(kb + k);
               const uint32_t sb = smem_u32(smem + stage * SP::kStageBytes);
@@ -459,19 +520,24 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
             const uint32_t sa = smem_u32(smem + stage * SP::kStageBytes);
             const CUtensorMap* am = p.amaps + e.x;
             const uint32_t sb = sa + (SPLIT ? 2 : 1) * SP::kABytes;
+            const bool need_b = k >= kpre;
             if (PAIR) {
               // every byte of both CTAs lands on the LEADER's barrier
-              if (leader) mbar_expect_tx(fb, 2 * SP::kStageBytes); else mbar_arrive_rank0(fb);
+              if (need_b) { if (leader) mbar_expect_tx(fb, 2 * SP::kStageBytes); else mbar_arrive_rank0(fb); }
               tma_load_4d_pair(sa, am, fb, e.y, x0 + e.w, y0 + e.z, img);
               if (SPLIT) tma_load_4d_pair(sa + SP::kABytes, am + 1, fb, e.y, x0 + e.w, y0 + e.z, img);
-              tma_load_2d_pair(sb, &bmap_hi, fb, k * kBK, brow);
-              if (SPLIT) tma_load_2d_pair(sb + SP::kBBytes, &bmap_lo, fb, k * kBK, brow);
+              if (need_b) {
+                tma_load_2d_pair(sb, &bmap_hi, fb, k * kBK, brow);
+                if (SPLIT) tma_load_2d_pair(sb + SP::kBBytes, &bmap_lo, fb, k * kBK, brow);
+              }
             } else {
-              mbar_expect_tx(fb, SP::kStageBytes);
+              if (need_b) mbar_expect_tx(fb, SP::kStageBytes);
               tma_load_4d(sa, am, fb, e.y, x0 + e.w, y0 + e.z, img);
               if (SPLIT) tma_load_4d(sa + SP::kABytes, am + 1, fb, e.y, x0 + e.w, y0 + e.z, img);
-              tma_load_2d(sb, &bmap_hi, fb, k * kBK, brow);
-              if (SPLIT) tma_load_2d(sb + SP::kBBytes, &bmap_lo, fb, k * kBK, brow);
+              if (need_b) {
+                tma_load_2d(sb, &bmap_hi, fb, k * kBK, brow);
+                if (SPLIT) tma_load_2d(sb + SP::kBBytes, &bmap_lo, fb, k * kBK, brow);
+              }
             }
           }
           __syncwarp();
@@ -615,7 +681,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         for (int i = et; i < BN; i += kAccThreads) {
           s_bias[i] = p.bias[n0 + i];
           s_scale[i] = p.scale[n0 + i];
-          s_shift[i] = p.shift[n0 + i] + (p.gadd ? p.gadd[(size_t)img * p.gadd_ld + n0 + i] * p.gadd_mult : 0.f);
+          // pairs: the dummy tile of an odd tile count has img == n_img -> clamp (its rows are never stored)
+          const int gi = img < p.n_img ? img : p.n_img - 1;
+          s_shift[i] = p.shift[n0 + i] + (p.gadd ? p.gadd[(size_t)gi * p.gadd_ld + n0 + i] * p.gadd_mult : 0.f);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         staged_key = vkey;
@@ -680,14 +748,15 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       //      (deterministic).  Arrive/depart counters reset themselves for the next launch / graph replay. ----
       if (S > 1) {
         // workspace layout [work item][column quad][row] (float4): lanes = rows -> 512-byte coalesced
-        float4* wp = reinterpret_cast<float4*>(p.ws) + ((size_t)w * (MT * BN / 4) + t_base / 4) * kBM + row;
+        // pairs: each CTA of the pair parks / reduces its own 128 rows (slot = work item * CG + rank)
+        float4* wp = reinterpret_cast<float4*>(p.ws) + ((size_t)(w * CG + (int)cta_rank) * (MT * BN / 4) + t_base / 4) * kBM + row;
 #pragma unroll
         for (int j = 0; j < CH; j += 4)
           __stcg(wp + (size_t)(j / 4) * kBM, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
         __threadfence();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
-          int* cnt = p.counters + 2 * tile;
+          int* cnt = p.counters + 2 * (tile * CG + (int)cta_rank);
           atomicAdd(cnt, 1);
           const long long t0 = clock64();
           int seen;
@@ -704,7 +773,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           for (int j = 0; j < 32; ++j) acc[ch + j] = 0.f;
           for (int q = 0; q < S; ++q) {
             const float4* rp = reinterpret_cast<const float4*>(p.ws) +
-                               ((size_t)(tile * S + q) * (MT * BN / 4) + (t_base + ch) / 4) * kBM + row;
+                               ((size_t)((tile * S + q) * CG + (int)cta_rank) * (MT * BN / 4) + (t_base + ch) / 4) * kBM + row;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 v = __ldcg(rp + (size_t)(j / 4) * kBM);
@@ -716,7 +785,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       // ---- epilogue on the register accumulators, 32 output channels at a time.  The output kind is uniform for
       //      the launch, so the branch sits outside the slab loops; the per-channel vectors are read with
       //      ld.shared (warp-uniform 16-byte reads), never through generic addressing. ----
-      const uint32_t sv = smem_u32(s_bias) + (uint32_t)c_base * 4u;   // bias | +BN*4: scale | +2*BN*4: shift
+      const uint32_t sv = epi_token(smem_u32(s_bias) + (uint32_t)c_base * 4u);   // bias | +BN*4: scale | +2*BN*4: shift
       const float neg_slope = p.act == ACT_RELU ? 0.f : (p.act == ACT_LEAKY02 ? 0.2f : 1.f);
       auto slab = [&](const int ch, float (&f)[32]) {
 #pragma unroll
@@ -737,7 +806,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       };
       if (p.wout) {
         // fused model_out: conv1x1(128->2) + tanh, x110 (model.py:108-109,175)
-        const uint32_t sh = smem_u32(s_head) + (uint32_t)c_base * 4u;
+        const uint32_t sh = epi_token(smem_u32(s_head) + (uint32_t)c_base * 4u);
         float h0 = 0.f, h1 = 0.f;
 #pragma unroll
         for (int ch = 0; ch < CH; ch += 32) {
@@ -854,7 +923,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       if (S > 1) {
         asm volatile("bar.sync 1, 256;" ::: "memory");          // all of this CTA's workspace reads are done
         if (et == 0) {
-          int* cnt = p.counters + 2 * tile;
+          int* cnt = p.counters + 2 * (tile * CG + (int)cta_rank);
           if (atomicAdd(cnt + 1, 1) == S - 1) { cnt[0] = 0; cnt[1] = 0; __threadfence(); }
         }
       }
@@ -906,6 +975,7 @@ struct UmmaPlan {
   CUtensorMap bmap_hi, bmap_lo;
   UmmaParams prm{};
   int num_sms = 148;
+  int dev = 0;
   int mt = 1;               // M-tiles (128 pixels each) per CTA tile
   int cg = 1;               // 2: CTA pairs (cta_group::2), one 256x256 output tile per pair
   int split_k = 1;
@@ -922,14 +992,14 @@ struct ViewKey {
 static int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
 template <int BN, int MT, int CG, bool SPLIT, bool HALO = false>
-static cudaError_t launch_inst(const UmmaPlan& pl, const UmmaParams& prm, cudaStream_t st) {
+static cudaError_t launch_inst(const UmmaPlan& pl, const UmmaParams& prm, cudaStream_t st, bool pdl) {
   using SP = SmemPlan<BN, MT, CG, SPLIT, HALO>;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_devs = 0;       // the opt-in is per device: one bit per device ordinal
+  if (pl.dev >= 64 || !(attr_devs & (1ull << pl.dev))) {
     cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<BN, MT, CG, SPLIT, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SP::kTotal);
     if (e != cudaSuccess) return e;
-    attr = true;
+    if (pl.dev < 64) attr_devs |= 1ull << pl.dev;
   }
   const long items = (long)prm.total_tiles * prm.split_k;
   int grid = items * CG < pl.num_sms ? (int)items * CG : (pl.num_sms / CG) * CG;
@@ -938,11 +1008,20 @@ static cudaError_t launch_inst(const UmmaPlan& pl, const UmmaParams& prm, cudaSt
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = SP::kTotal;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (CG > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = CG; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {   // may start while the previous kernel of the forward drains (see pdl_wait in the kernel)
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = CG > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, umma_conv_kernel<BN, MT, CG, SPLIT, HALO>, pl.bmap_hi, pl.bmap_lo, prm);
 }
 
@@ -955,6 +1034,7 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, c->dev);
   pl->num_sms = prop.multiProcessorCount;
+  pl->dev = c->dev;
   // tile geometry
   op.bn_tile = (op.cout_pad % 256 == 0) ? 256 : (op.cout_pad % 192 == 0) ? 192 : (op.cout_pad % 128 == 0) ? 128 : 64;
   if (op.cout_pad % op.bn_tile) { c->err = "cout not tileable: " + op.name; return IDC_ERR_ARG; }
@@ -968,11 +1048,10 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   // shared-memory-bandwidth bound with per-tap boxes) load one 18x10-pixel halo tile per 64 input channels instead of
   // one box per tap, when the launch fills the machine.  Measured at 64 x 256^2: c2_2 0.76 -> 0.63 ms, c9_2 0.76 ->
   // 0.63, c10_2 2.44 -> 2.28; the 64-column c1_2 gets slower (1.11 -> 1.17: its weight tile is re-streamed per 128
-  // instead of 256 pixels) and keeps the per-tap path.  IDC_HALO=0 turns it off, =3 forces it on every eligible op
+  // instead of 256 pixels) and keeps the per-tap path.  option halo=0 turns it off, =3 forces it on every eligible op
   // (also 64 columns, also tiny launches) for the unit tests.
   {
-    int mode = 1;
-    if (const char* e = getenv("IDC_HALO")) mode = atoi(e);
+    const int mode = c->opt.halo;
     bool ok = mode >= 1 && !c->fast && op.ncls == 1 && op.ntaps == 9 && (op.bn_tile == 128 || (mode >= 3 && op.bn_tile == 64));
     unsigned seen = 0;
     for (int t = 0; ok && t < op.ntaps; ++t) {
@@ -997,20 +1076,54 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
                         (op.cout_pad / op.bn_tile);
     if (tiles2 >= 2L * pl->num_sms && op.hbox * 2 <= 256) pl->mt = 2;
   }
-  if (const char* e = getenv("IDC_MT")) { int v = atoi(e); if (!pl->halo && (v == 1 || (v == 2 && op.bn_tile <= 128))) pl->mt = v; }
+  { const int v = c->opt.mt; if (!pl->halo && (v == 1 || (v == 2 && op.bn_tile <= 128))) pl->mt = v; }
   // CTA pairs for the 256-wide tiles when the launch is large (never on the split-K / batch-1 path)
   pl->cg = 1;
   {
     const long tiles1 = (long)op.ncls * c->max_n * ceil_div(op.Hl, op.hbox) * ceil_div(op.Wl, op.wbox) * (op.cout_pad / op.bn_tile);
     const bool can = !c->fast && (op.bn_tile == 256 || op.bn_tile == 128 || (op.bn_tile == 64 && (pl->mt == 2 || pl->halo)));
     const long tiles_mt = tiles1 / pl->mt;
-    int mode = 1;          // IDC_PAIRS: 0 = off, 1 (default) = launches that give every SM pair >= 2 tiles, 2 = always
-    if (const char* e = getenv("IDC_PAIRS")) mode = atoi(e);
+    const int mode = c->opt.pairs;   // 0 = off, 1 (default) = launches that give every SM pair >= 2 tiles, 2 = always
     if (can && (mode >= 2 || (mode == 1 && tiles_mt >= 4L * pl->num_sms))) pl->cg = 2;
+  }
+  const int nkb = op.K / kBK;
+  // split-K for launches that cannot fill the machine even at the ctx's max batch (interactive path): K is cut into S
+  // slices per tile, all work items co-resident.  With `split_pairs` the slices run as CTA pairs (cta_group::2): per
+  // k-block an SM then fetches 64 KB of operands instead of 96 KB -- at batch 1 these launches are bound by the
+  // L2 -> SM operand traffic (every CTA re-fetches its A and B tiles), not by the tensor pipe.
+  {
+    const int ty = ceil_div(op.Hl, op.hbox * pl->mt), tx = ceil_div(op.Wl, op.wbox), ntn = op.cout_pad / op.bn_tile;
+    const long m_tiles = (long)c->max_n * ty * tx;
+    const long T = (long)op.ncls * m_tiles * ntn;
+    int S = 1;
+    const bool eligible = nkb >= 8 && !op.fuse_out_head && pl->mt == 1 && pl->cg == 1 && !pl->halo;
+    if (T * 2 <= pl->num_sms && eligible) {
+      S = (int)(pl->num_sms / T);
+      if (S > nkb / 4) S = nkb / 4;
+      if (S > op.bn_tile / 32) S = op.bn_tile / 32;      // one 32-column piece per CTA at least
+      if (S < 1) S = 1;
+    }
+    {                                                      // experiments; must keep all work items co-resident
+      const int v = c->opt.split_k;
+      if (v >= 1 && v <= nkb && v <= op.bn_tile / 32 && pl->mt == 1 && !pl->halo && pl->cg == 1 && T * v <= pl->num_sms) S = v;
+    }
+    long Tw = T;
+    if (S > 1 && c->opt.split_pairs && !c->fast && (op.bn_tile == 256 || op.bn_tile == 128)) {
+      const long T2 = (long)op.ncls * ((m_tiles + 1) / 2) * ntn;
+      int S2 = (int)((pl->num_sms / 2) / T2);
+      if (S2 > nkb / 4) S2 = nkb / 4;
+      if (S2 > op.bn_tile / 32) S2 = op.bn_tile / 32;
+      if (c->opt.split_k >= 1 && c->opt.split_k <= S2) S2 = c->opt.split_k;
+      if (S2 >= 2) { pl->cg = 2; S = S2; Tw = T2 * 2; }
+    }
+    pl->split_k = S;
+    pl->ws_tiles = (int)Tw;                                // reduction slots: (pair-)tiles x CTAs per tile
+    pl->ws_floats = S > 1 ? (size_t)Tw * S * kBM * op.bn_tile : 0;
+    if (pl->ws_floats > c->splitk_ws_floats) c->splitk_ws_floats = pl->ws_floats;
+    if (S > 1 && pl->ws_tiles > c->splitk_max_tiles) c->splitk_max_tiles = pl->ws_tiles;
   }
   // views + k-block table
   std::vector<ViewKey> views;
-  const int nkb = op.K / kBK;
   std::vector<int4> kblk((size_t)op.ncls * nkb);
   if (pl->halo) {
     // k-block i = (input group i / 9, tap i % 9); entry = {-, K column of the weight tile, dy + 1, dx + 1}
@@ -1095,7 +1208,7 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   cudaMemcpy(pl->d_kblk, kblk.data(), kblk.size() * sizeof(int4), cudaMemcpyHostToDevice);
 
   UmmaParams& q = pl->prm;
-  q.amaps = pl->d_amaps; q.kblk = pl->d_kblk; q.nkb = nkb; q.ncls = op.ncls;
+  q.amaps = pl->d_amaps; q.n_amaps = (int)amaps.size(); q.kblk = pl->d_kblk; q.nkb = nkb; q.ncls = op.ncls;
   q.halo_groups = pl->halo ? nkb / 9 : 0;
   {
     // chunk_kb: k-blocks summed inside the tensor core before the FP32 round-to-nearest add.
@@ -1104,7 +1217,7 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
     // one k-block of MMA time at 256 output columns per CTA tile; the Cout<=128 layers have short K
     // (few chunks per tile to amortise the tile epilogue), so they use 2 -> 2.1e-4 end to end.
     int g = c->fast ? 4 : (op.bn_tile <= 128 ? 2 : 1);
-    if (const char* e = getenv("IDC_CHUNK_KB")) { int v = atoi(e); if (v >= 1) g = v; }
+    if (c->opt.chunk_kb >= 1) g = c->opt.chunk_kb;
     q.chunk_kb = g;
   }
   q.tiles_y = ceil_div(op.Hl, op.hbox * pl->mt); q.tiles_x = ceil_div(op.Wl, op.wbox);
@@ -1125,30 +1238,10 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   }
   if (op.fuse_out_head) { q.wout = c->wout; q.bout = c->bout; }
   q.store_mode = 1;
-  if (const char* e = getenv("IDC_DIRECT_STORES")) { if (atoi(e)) q.store_mode = 0; }
+  if (c->opt.direct_stores) q.store_mode = 0;
   q.err = c->d_err;
   q.img0 = 0;
   q.dbgbuf = nullptr;
-  // split-K for launches that cannot fill the machine even at the ctx's max batch (interactive path)
-  {
-    const long T = (long)op.ncls * c->max_n * q.tiles_y * q.tiles_x * q.n_tiles_n;
-    int S = 1;
-    if (T * 2 <= pl->num_sms && nkb >= 8 && !op.fuse_out_head && pl->mt == 1 && pl->cg == 1 && !pl->halo) {
-      S = (int)(pl->num_sms / T);
-      if (S > nkb / 4) S = nkb / 4;
-      if (S > op.bn_tile / 32) S = op.bn_tile / 32;      // one 32-column piece per CTA at least
-      if (S < 1) S = 1;
-    }
-    if (const char* e = getenv("IDC_SPLIT_K")) {           // experiments; must keep all work items co-resident
-      int v = atoi(e);
-      if (v >= 1 && v <= nkb && v <= op.bn_tile / 32 && pl->mt == 1 && !pl->halo && T * v <= pl->num_sms) S = v;
-    }
-    pl->split_k = S;
-    pl->ws_tiles = (int)T;
-    pl->ws_floats = S > 1 ? (size_t)T * S * kBM * op.bn_tile : 0;
-    if (pl->ws_floats > c->splitk_ws_floats) c->splitk_ws_floats = pl->ws_floats;
-    if (S > 1 && pl->ws_tiles > c->splitk_max_tiles) c->splitk_max_tiles = pl->ws_tiles;
-  }
   return IDC_OK;
 }
 
@@ -1186,15 +1279,16 @@ cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float ou
   if (op.fuse_out_head && !out_ab_fused) return cudaErrorInvalidValue;
   c->launch_count++;
   const bool split = !c->fast;
+  const bool pdl = pdl_take(c);
 #define IDC_LAUNCH(BN_, MT_, CG_)                                              \
-  return split ? launch_inst<BN_, MT_, CG_, true>(*pl, prm, st) : launch_inst<BN_, MT_, CG_, false>(*pl, prm, st)
+  return split ? launch_inst<BN_, MT_, CG_, true>(*pl, prm, st, pdl) : launch_inst<BN_, MT_, CG_, false>(*pl, prm, st, pdl)
   if (pl->halo) {
     if (!split) return cudaErrorInvalidValue;
     switch (op.bn_tile * 10 + pl->cg) {
-      case 641: return launch_inst<64, 1, 1, true, true>(*pl, prm, st);
-      case 642: return launch_inst<64, 1, 2, true, true>(*pl, prm, st);
-      case 1281: return launch_inst<128, 1, 1, true, true>(*pl, prm, st);
-      case 1282: return launch_inst<128, 1, 2, true, true>(*pl, prm, st);
+      case 641: return launch_inst<64, 1, 1, true, true>(*pl, prm, st, pdl);
+      case 642: return launch_inst<64, 1, 2, true, true>(*pl, prm, st, pdl);
+      case 1281: return launch_inst<128, 1, 1, true, true>(*pl, prm, st, pdl);
+      case 1282: return launch_inst<128, 1, 2, true, true>(*pl, prm, st, pdl);
       default: return cudaErrorInvalidValue;
     }
   }

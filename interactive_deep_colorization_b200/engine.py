@@ -19,7 +19,9 @@ class LhnContext(object):
     `SIGGRAPHGenerator(...).cuda().eval()`, /root/reference/data/colorize_image.py:221-232)."""
 
     def __init__(self, device=0, max_n=1, H=256, W=256, dist=False, engine="tcgen05", fast_fp16=False,
-                 global_hints=False, use_graph=True, keep_conv10=False, caffe313=False):
+                 global_hints=False, use_graph=True, keep_conv10=False, caffe313=False, options=None):
+        """options: {name: int} plan-time switches, see include/idc_b200.h: idc_set_option
+        (halo, pairs, mt, chunk_kb, split_k, split_pairs, direct_stores, host_pipe, pdl)."""
         self.lib = _lib.load()
         flags = 0
         if dist:
@@ -47,6 +49,11 @@ class LhnContext(object):
                                     "required; there is no CPU fallback" % (device, max_n, H, W))
         self.h = h
         self.ready = False
+        for k, v in (options or {}).items():
+            self.set_option(k, v)
+
+    def set_option(self, name, value):
+        _lib.check(self.h, self.lib.idc_set_option(self.h, name.encode(), int(value)))
 
     # ---- weights ---------------------------------------------------------------------------
     def load_state_dict(self, sd):
@@ -105,9 +112,11 @@ class LhnContext(object):
         return {"ab": out_ab, "dist": out_dist if want_dist else None, "rgb": out_rgb if want_rgb else None}
 
     def forward_host(self, L_mc, ab, mask, maskcent=0.0, glob=None, want_dist=False, want_rgb=False,
-                     out_ab=None, out_dist=None, out_rgb=None):
+                     out_ab=None, out_dist=None, out_rgb=None, want_abq=False):
         """numpy float32 C-contiguous host arrays (pinned or pageable) -> dict of numpy arrays.
-        Synchronous; includes H2D + D2H."""
+        Synchronous; includes H2D + D2H.  want_abq: also the reference's quantised output_ab
+        (rgb2lab(rgb)[1:], float64; implies want_rgb)."""
+        want_rgb = want_rgb or want_abq
         n = L_mc.shape[0]
         for a in (L_mc, ab, mask):
             assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
@@ -117,12 +126,15 @@ class LhnContext(object):
             out_dist = np.empty((n, 529, self.H // 4, self.W // 4), np.float32)
         if want_rgb and out_rgb is None:
             out_rgb = np.empty((n, self.H, self.W, 3), np.uint8)
-        rc = self.lib.idc_forward_host(self.h, n, self.H, self.W, _np_ptr(L_mc), _np_ptr(ab), _np_ptr(mask),
-                                       float(maskcent), _np_ptr(glob) if glob is not None else None,
-                                       _np_ptr(out_ab), _np_ptr(out_dist) if want_dist else None,
-                                       _np_ptr(out_rgb) if want_rgb else None)
+        out_abq = np.empty((n, 2, self.H, self.W), np.float64) if want_abq else None
+        rc = self.lib.idc_forward_host_q(self.h, n, self.H, self.W, _np_ptr(L_mc), _np_ptr(ab), _np_ptr(mask),
+                                         float(maskcent), _np_ptr(glob) if glob is not None else None,
+                                         _np_ptr(out_ab), _np_ptr(out_dist) if want_dist else None,
+                                         _np_ptr(out_rgb) if want_rgb else None,
+                                         _np_ptr(out_abq) if want_abq else None)
         _lib.check(self.h, rc)
-        return {"ab": out_ab, "dist": out_dist if want_dist else None, "rgb": out_rgb if want_rgb else None}
+        return {"ab": out_ab, "dist": out_dist if want_dist else None, "rgb": out_rgb if want_rgb else None,
+                "abq": out_abq}
 
     def set_dist_resident(self, on=True):
         """Interactive mode: the dist head runs on every forward_host but stays on the device."""

@@ -307,12 +307,8 @@ def test_odd_geometries(synth_sd, H, W, n):
         ab[i, :, y:y + 3, x:x + 3] = rs.uniform(-80, 80, (2, 1, 1))
         m[i, :, y:y + 3, x:x + 3] = 1
     ref = util.oracle_forward(synth_sd, L, ab, m, 0.5, dist=True)
-    for forced_pairs in ("0", "2"):
-        util.os.environ["IDC_PAIRS"] = forced_pairs
-        try:
-            ctx = util.make_ctx(synth_sd, H, W, max_n=n, dist=True)
-        finally:
-            del util.os.environ["IDC_PAIRS"]
+    for forced_pairs in (0, 2):
+        ctx = util.make_ctx(synth_sd, H, W, max_n=n, dist=True, options={"pairs": forced_pairs})
         r = ctx.forward_host(L, ab, m, 0.5, want_dist=True, want_rgb=True)
         assert util.maxabs(r["ab"], ref[0]) <= TOL_AB, (H, W, forced_pairs)
         assert util.maxabs(r["dist"], ref[1]) < 1e-5

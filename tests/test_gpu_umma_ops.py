@@ -13,19 +13,14 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module", params=[(1, 0, 0), (2, 0, 0), (1, 2, 0), (2, 2, 0), (1, 0, 3), (1, 2, 3)],
                 ids=["mt1", "mt2", "pairs", "pairs_mt2", "halo", "halo_pairs"])
 def setup(request, synth_sd):
-    """(IDC_MT, IDC_PAIRS, IDC_HALO) are read when the launch plan is built: the 128-pixel tiles, the 256-pixel
+    """The plan-time options (mt, pairs, halo) are applied when the launch plan is built: the 128-pixel tiles, the 256-pixel
     tiles, the cta_group::2 pair path (forced, incl. the odd-tile-count dummy tile) and the halo-tile
     A operand (one TMA tile per 64 input channels + pixel-shifted UMMA descriptors, stride-1 3x3 layers with
     <= 128 output columns) are exercised on every op that supports them."""
-    import os
     L, ab, m = util.small_batch(3, 64, seed=300)
     _, inter = util.oracle_forward(synth_sd, L, ab, m, 0.5, dist=False, intermediates=True)
-    os.environ["IDC_MT"], os.environ["IDC_PAIRS"] = str(request.param[0]), str(request.param[1])
-    os.environ["IDC_HALO"] = str(request.param[2])
-    try:
-        ctx = util.make_ctx(synth_sd, 64, 64, max_n=3, engine="tcgen05", keep_conv10=True, use_graph=False)
-    finally:
-        del os.environ["IDC_MT"], os.environ["IDC_PAIRS"], os.environ["IDC_HALO"]
+    ctx = util.make_ctx(synth_sd, 64, 64, max_n=3, engine="tcgen05", keep_conv10=True, use_graph=False,
+                        options={"mt": request.param[0], "pairs": request.param[1], "halo": request.param[2]})
     yield ctx, inter
     ctx.close()
 

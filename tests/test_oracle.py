@@ -94,3 +94,18 @@ def test_oracle_vs_live_reference(synth_sd):
     # state_dict key compatibility of the drop-in module
     from interactive_deep_colorization_b200.model import SIGGRAPHGeneratorB200
     assert set(SIGGRAPHGeneratorB200(dist=True).state_dict().keys()) == set(net.state_dict().keys())
+
+
+def test_global_stats_encode_pinned_to_reference_nnenc():
+    """Row f3: the nearest-bin encode + global average of oracle/caffe_spec.global_stats against the output of the
+    reference's own NNEncode(NN=1, sigma=5) class (caffe_files/color_quantization.py:6-38, what NNEncLayer wraps,
+    caffe_traininglayers.py:161-196), stored by tests/golden/make_glob_golden.py."""
+    from oracle import caffe_spec
+    g = util.golden("glob_nnenc.npz")
+    pts = np.load(util.os.path.join(util.GOLDEN, "pts_in_hull.npy"))
+    for name in ("mortar", "rand"):
+        got = caffe_spec.global_stats(g[name + "_rgb"], pts)
+        cells = g[name + "_bin"].size
+        near_boundary = int((g[name + "_margin"] < 1e-3).sum())          # FP32 vs FP64 distance ties
+        assert np.abs(got[:313] - g[name + "_hist"]).sum() * cells / 2 <= near_boundary + 1e-3   # float32 storage of the histogram
+        assert abs(got[:313].sum() - 1.0) < 1e-6 and got[313] == 1.0 and got[315] == 1.0

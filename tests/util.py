@@ -35,6 +35,7 @@ def oracle_forward(sd, L, ab, mask, maskcent=0.0, dist=False, glob_add=None, int
 
 
 def make_ctx(sd, H, W, max_n=1, **kw):
+    """kw may carry options={...} (plan-time switches, idc_set_option): applied before the weights are packed."""
     from interactive_deep_colorization_b200.engine import LhnContext
     ctx = LhnContext(device=0, max_n=max_n, H=H, W=W, **kw)
     ctx.load_state_dict(sd)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""GPU tool: ab error and time of the tcgen05 engine as a function of IDC_CHUNK_KB (k-blocks summed
+"""GPU tool: ab error and time of the tcgen05 engine as a function of the chunk_kb option (k-blocks summed
 inside the tensor core before the FP32 round-to-nearest add).  Writes a small table for profiles/."""
 import os
 import sys
@@ -23,8 +23,7 @@ def main():
     Lb, abb, mb = synth.synthetic_batch(16, 256, seed=0)
     print("chunk_kb | max|d ab| golden rand5 | ms / 16-image forward")
     for chunk in (1, 2, 4, 8, 100000):
-        os.environ["IDC_CHUNK_KB"] = str(chunk)
-        ctx = util.make_ctx(sd, 256, 256, max_n=16, use_graph=False)
+        ctx = util.make_ctx(sd, 256, 256, max_n=16, use_graph=False, options={"chunk_kb": chunk})
         r = ctx.forward_host(L, ab[None].astype(np.float32), m[None].astype(np.float32), 0.5)
         err = util.maxabs(r["ab"][0], ref)
         dL, dab, dm = util.dev(Lb), util.dev(abb), util.dev(mb)
@@ -38,7 +37,6 @@ def main():
         ms = (time.perf_counter() - t0) / 5 * 1e3
         print("%8s | %.3e | %.3f" % (chunk if chunk < 1000 else "all", err, ms))
         ctx.close()
-    del os.environ["IDC_CHUNK_KB"]
 
 
 if __name__ == "__main__":
