@@ -2,15 +2,25 @@
 """bench.py -- net_forward images/sec @256x256 (BASELINE.json metric) + p50 single-click latency.
 
     python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU)
-    python bench.py --impl reference --steps K --warmup W    # CPU baseline arm (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path
 
-A step = ONE forward of the hot path (pack+conv1_1 -> conv trunk -> regression head) over one
-batch of synthetic 256x256 L + sparse-hint inputs (BASELINE config 3: 64 images / GPU, weak
-scaling).  `value` = images/s with inputs resident in HBM, device-timed with CUDA events, max over
-ranks.  `e2e` = the same through the host-pointer C-ABI call (pinned H2D of the inputs + D2H of
-the ab maps inside the timed region).  The reference arm times the CPU restatement of the
-reference network (oracle/lhn_ref.py -- the reference is Python/torch and /root/reference does
-not exist on the GPU box) looping single-image calls as the reference does (model.py:139-141).
+A step = ONE forward of the hot path (pack+conv1_1 -> conv trunk -> regression head) over one batch of synthetic
+256x256 L + sparse-hint inputs (BASELINE config 3: 64 images / GPU, weak scaling).
+  value    images/s with the inputs resident in HBM: K replays of the CUDA-graph-captured forward (the shipped
+           configuration: no per-op events, kernels chained by programmatic dependent launch), device-timed with CUDA
+           events, max over ranks.  Per-op times come from a SEPARATE, untimed profiling pass.
+  e2e      the same through the host-pointer C-ABI call (pinned H2D of the inputs + D2H of the ab maps inside the
+           timed region).
+  config4  BASELINE config 4 as an extra record at every --gpus N: 512x512, GLOBAL batch 16 with a global-hints
+           vector per image, sharded 16/N per GPU (strong scaling: 1 vs 8 GPUs).
+  latency  BASELINE config 5 (20 sequential put_point -> forward, dist head on): p50/p99 of the C-ABI click call and
+           of the wrapper-level calls the GUI makes (ui/gui_draw.py:258-286).
+Every rank also runs ONE fixed-seed image outside the timed region; rank 0 asserts that all ranks produced the same
+bytes (the rank != 0 weight path: reserve -> broadcast -> adopt).
+The reference arm times the UNMODIFIED reference wrapper `ColorizeImageTorch.net_forward` (staged by
+`__graft_entry__.build()` into the git-ignored oracle/_ref/, kind "reference") on the host cores, looping single-image
+calls as the reference does (models/pytorch/model.py:139-141); without the staged copy it falls back to the CPU oracle
+port (oracle/lhn_ref.py, kind "port").
 """
 import argparse
 import json
@@ -30,16 +40,16 @@ if ROOT not in sys.path:
 METRIC = "net_forward images/sec @256x256"   # --size 512 reports the same metric name with the size in config
 X = 256
 PER_GPU_BATCH = 64
+NCU_TRAFFIC_CSV = os.path.join(ROOT, "profiles", "r02_ncu_full_umma_conv_batch64.csv")
 
 
 def _ncu_traffic(batch, size):
-    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this same workload (profiles/r01_ncu_full_umma_conv_batch64.csv)."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_full_umma_conv_batch64.csv")
-    if batch != 64 or size != 256 or not os.path.isfile(p):
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed `ncu --set full`
+    capture of this same workload at HEAD (profiles/r02_ncu_full_umma_conv_batch64.csv)."""
+    if batch != 64 or size != 256 or not os.path.isfile(NCU_TRAFFIC_CSV):
         return None
     tot, n = 0.0, 0
-    for line in open(p):
+    for line in open(NCU_TRAFFIC_CSV):
         if line.startswith("#") or line.startswith("op,"):
             continue
         f = line.strip().split('",')
@@ -58,6 +68,17 @@ def _peaks():
         return {"tensor": d.get("bf16_tflops_sustained", 1370.8), "tensor_burst": d.get("bf16_tflops", 1653.3),
                 "hbm": d.get("hbm_gbs", 6569.6), "src": "measured (MEASURED_PEAKS.json, sustained bf16 cuBLAS)"}
     return {"tensor": 1400.0, "tensor_burst": 1590.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+def workload_config(N, size, world):
+    """`config` of the JSON line -- identical for both arms (the reference arm describes its bounded sample in
+    cpu_baseline.sample, not here)."""
+    return {"workload": "BASELINE config %s: %d x %dx%d synthetic L + 0-10 sparse 7x7 ab hints per GPU, "
+                        "regression head (ab map)" % ("3" if size == 256 else "4 (no global hints)", N, size, size),
+            "per_gpu_batch": N, "global_batch": N * world,
+            "parallelism": "dp%d (image sharding, no per-step collective)" % world,
+            "l2_policy": "per-step working set (~%.1f GB of activations) >> 126 MB L2; inputs are not re-used from L2"
+                         % (N * 0.15 * (size / 256.0) ** 2)}
 
 
 class ClockSampler(threading.Thread):
@@ -104,68 +125,242 @@ class ClockSampler(threading.Thread):
                                    if any(len(s) > 6 for s in self.samples) else None)}
 
 
-def cpu_baseline_run(sd, budget_s, max_images, nthreads=None):
-    """Reference CPU path (oracle port) on the host cores: loop of single-image forwards, as the
-    reference has no batch API (model.py:139-141).  Returns (images/s, images, threads)."""
-    import torch
-    from oracle import lhn_ref, synth
-    if nthreads:
-        torch.set_num_threads(nthreads)
-    L, ab, m = synth.synthetic_batch(min(max_images, 8), X, seed=0, max_hints=10)
-    with torch.no_grad():
-        lhn_ref.lhn_forward(sd, L[:1], ab[:1], m[:1], 0.5)          # warm-up (oneDNN primitive cache)
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference's own code when staged (oracle/_ref), else the oracle port
+# ----------------------------------------------------------------------------------------------
+class CpuArm(object):
+    """One single-image CPU forward per call, as the reference runs it (batch 1, models/pytorch/model.py:139-141)."""
+
+    def __init__(self):
+        import torch
+        from oracle import ref_shims, synth
+        self.torch, self.synth = torch, synth
+        self.sd = synth.torch_state_dict(1234)
+        self.kind = "port"
+        self.cm = None
+        if ref_shims.reference_available():
+            try:
+                import tempfile
+                CI = ref_shims.import_reference_wrapper()
+                wpath = os.path.join(tempfile.mkdtemp(), "synthetic_1234.pth")
+                torch.save(self.sd, wpath)
+                import contextlib
+                import io
+                with contextlib.redirect_stdout(io.StringIO()):
+                    cm = CI.ColorizeImageTorch(Xd=X, maskcent=True)
+                    cm.prep_net(path=wpath)
+                    cm.set_image(np.random.RandomState(0).randint(0, 256, (X, X, 3)).astype(np.uint8))
+                self.cm, self.kind = cm, "reference"
+            except Exception as e:                      # staged copy unusable: fall back to the port, say why
+                sys.stderr.write("reference wrapper unavailable (%r): timing the oracle port\n" % (e,))
+        self.L, self.ab, self.m = synth.synthetic_batch(8, X, seed=0, max_hints=10)
+
+    def describe(self):
+        if self.kind == "reference":
+            return ("the UNMODIFIED reference ColorizeImageTorch.net_forward (data/colorize_image.py:249-268: net forward with "
+                    "autograd on as the reference calls it + Lab->RGB + RGB->Lab post-process), staged in oracle/_ref")
+        return "CPU oracle port of SIGGRAPHGenerator.forward (oracle/lhn_ref.py, torch fp32, no_grad, no post-process)"
+
+    def one(self, i):
+        i %= self.L.shape[0]
+        if self.cm is not None:
+            self.cm.net_forward(self.ab[i].astype(np.float64), self.m[i].astype(np.float64))
+        else:
+            from oracle import lhn_ref
+            with self.torch.no_grad():
+                lhn_ref.lhn_forward(self.sd, self.L[i:i + 1], self.ab[i:i + 1], self.m[i:i + 1], 0.5)
+
+    def run(self, budget_s, max_images, nthreads=None):
+        """-> (images/s, images, threads)"""
+        if nthreads:
+            self.torch.set_num_threads(nthreads)
+        self.one(0)                                      # warm-up (oneDNN primitive cache)
         t0, n = time.perf_counter(), 0
         while n < max_images and (time.perf_counter() - t0) < budget_s:
-            i = n % L.shape[0]
-            lhn_ref.lhn_forward(sd, L[i:i + 1], ab[i:i + 1], m[i:i + 1], 0.5)
+            self.one(n)
             n += 1
-        dt = time.perf_counter() - t0
-    return n / dt, n, torch.get_num_threads()
+        return n / (time.perf_counter() - t0), n, self.torch.get_num_threads()
 
-
-def best_cpu_threads(sd):
-    """The reference uses torch's default thread pool; on a 128-core host the default (all cores) is
-    pathologically slow for batch-1 convs, so the baseline is run at the best of a few pool sizes."""
-    ncpu = os.cpu_count() or 1
-    best = (0.0, ncpu)
-    for t in sorted(set([min(ncpu, c) for c in (8, 16, 32, 64)] + [ncpu])):
-        ips, _, _ = cpu_baseline_run(sd, 4.0, 2, t)
-        if ips > best[0]:
-            best = (ips, t)
-    return best[1]
+    def best_threads(self):
+        """The reference uses torch's default thread pool; on a 128-core host the default (all cores) is pathologically
+        slow for batch-1 convs, so the baseline runs at the best of a few pool sizes (favours the reference)."""
+        ncpu = os.cpu_count() or 1
+        best = (0.0, ncpu)
+        for t in sorted(set([min(ncpu, c) for c in (8, 16, 32, 64)] + [ncpu])):
+            ips, _, _ = self.run(4.0, 2, t)
+            if ips > best[0]:
+                best = (ips, t)
+        return best[1]
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import torch
-    from oracle import synth
-    sd = synth.torch_state_dict(1234)
-    nthr = best_cpu_threads(sd)
+    global X
+    X = args.size
+    arm = CpuArm()
+    nthr = arm.best_threads()
     per_step = 4                       # bounded sample: 4 single-image CPU forwards per step
     for _ in range(args.warmup):
-        cpu_baseline_run(sd, 1e9, 1, nthr)
+        arm.run(1e9, 1, nthr)
     t0 = time.perf_counter()
     n = 0
     for _ in range(args.steps):
-        _, k, thr = cpu_baseline_run(sd, 1e9, per_step, nthr)
+        _, k, thr = arm.run(1e9, per_step, nthr)
         n += k
     dt = time.perf_counter() - t0
     ips = n / dt
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE config 3: 64 x 256x256 synthetic L + 0-10 sparse 7x7 ab hints per GPU, "
-                                   "regression head (ab map)",
-                       "sample": "bounded: %d single-image calls of the CPU oracle port of SIGGRAPHGenerator.forward per step, "
-                                 "images drawn from that workload (the reference has no batch API, model.py:139-141)" % per_step},
-            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": thr, "kind": "port",
-                             "sample": "%d images (batch-1 loop), torch CPU fp32, best-of pool sizes -> %d threads of %d host cores"
-                                       % (n, thr, os.cpu_count() or 0)},
+            "config": workload_config(args.batch, X, args.gpus),
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": thr, "kind": arm.kind,
+                             "sample": "bounded: %d single-image calls per step (%d images in all) of %s; images drawn from the "
+                                       "config-3 workload (the reference has no batch API); best-of pool sizes -> %d threads of %d "
+                                       "host cores" % (per_step, n, arm.describe(), thr, os.cpu_count() or 0)},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def timed_graph_steps(torch, ctx, fwd, steps, warmup, barrier, dev):
+    """Capture ONE forward into a CUDA graph (torch capture of the stream the C ABI launches on) and time `steps`
+    replays with CUDA events.  Falls back to plain stream launches if capture is refused.  -> (ms_total, mode)"""
+    mode = "cuda graph replay (torch.cuda.graph capture of idc_forward; kernels chained by PDL)"
+    graph = None
+    try:
+        s = torch.cuda.Stream(dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            fwd()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fwd()
+    except Exception as e:
+        sys.stderr.write("graph capture refused (%r): timing stream launches\n" % (e,))
+        graph, mode = None, "stream launches (kernels chained by PDL)"
+        torch.cuda.synchronize(dev)
+    run = graph.replay if graph is not None else fwd
+    for _ in range(max(warmup, 3)):
+        run()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        run()
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    return e0.elapsed_time(e1), mode, (t0, t1)
+
+
+def run_config4(args, torch, dist, world, rank, local, dev, barrier, max_over_ranks):
+    """BASELINE config 4: 512x512, global batch 16, global-hints vector per image, 16/world images per GPU."""
+    from interactive_deep_colorization_b200.parallel import ShardedColorizer, shard_range
+    from oracle import caffe_spec, synth
+    G, S = 16, 512
+    start, count = shard_range(G, world, rank)
+    sd = None
+    if rank == 0 or world == 1:
+        sd = synth.torch_state_dict(1234)
+        sd.update({k: torch.from_numpy(v) for k, v in caffe_spec.synthetic_glob_state_dict().items()})
+    eng = ShardedColorizer(S, S, max(count, 1), state_dict=sd, device=local, dist_head=False, use_graph=False,
+                           global_hints=True)
+    ctx = eng.ctx
+    L, ab, m = synth.synthetic_batch(G, S, seed=40, max_hints=10)          # the same 16 images on every rank ...
+    ga, sat = synth.synthetic_glob(G, seed=3)
+    glob = np.ascontiguousarray(np.concatenate([ga, sat], axis=1).astype(np.float32))
+    sl = slice(start, start + count)                                         # ... each rank takes its slice
+    hL, hab, hm, hg = (torch.from_numpy(np.ascontiguousarray(a[sl])).pin_memory() for a in (L, ab, m, glob))
+    dL, dab, dm, dg = hL.to(dev), hab.to(dev), hm.to(dev), hg.to(dev)
+    out = torch.empty((count, 2, S, S), dtype=torch.float32, device=dev)
+    hout = torch.empty((count, 2, S, S), dtype=torch.float32).pin_memory()
+    ms_total, mode, _ = timed_graph_steps(torch, ctx, lambda: ctx.forward_device(dL, dab, dm, 0.5, glob=dg, out_ab=out),
+                                          args.steps, args.warmup, barrier, dev)
+    ms_step = max_over_ranks(ms_total, dev) / args.steps
+    for _ in range(2):
+        ctx.forward_host(hL.numpy(), hab.numpy(), hm.numpy(), 0.5, glob=hg.numpy(), out_ab=hout.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.forward_host(hL.numpy(), hab.numpy(), hm.numpy(), 0.5, glob=hg.numpy(), out_ab=hout.numpy())
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+    flops = ctx.flops_per_image()
+    ctx.close()
+    return {"workload": "BASELINE config 4: 512x512, GLOBAL batch 16 with a 316-entry global-hints vector per image, "
+                        "sharded %d image(s) per GPU over %d GPU(s)" % (count, world),
+            "value": G / (ms_step * 1e-3), "unit": "images/s", "ms_per_step": ms_step, "scaling": "strong",
+            "global_batch": G, "per_gpu_batch": count, "n_gpus": world,
+            "e2e": {"value": G * args.steps / e2e_s, "unit": "images/s",
+                    "h2d_bytes_per_step": int(G * (4 * S * S + 316) * 4), "d2h_bytes_per_step": int(G * 2 * S * S * 4)},
+            "useful_tflops": G * flops / (ms_step * 1e-3) / 1e12, "launch_mode": mode}
+
+
+def run_latency(local, L):
+    """BASELINE config 5 at two levels: the C-ABI click call and the wrapper calls the GUI makes."""
+    from interactive_deep_colorization_b200 import colorize_image as CI
+    from interactive_deep_colorization_b200.engine import LhnContext
+    from oracle import synth
+    sd = synth.torch_state_dict(1234)
+    lctx = LhnContext(device=local, max_n=1, H=X, W=X, dist=True)
+    lctx.load_state_dict(sd)
+    lctx.set_dist_resident(True)      # config 5: the click only needs dist[:, h//4, w//4]
+    rs = np.random.RandomState(0)
+    l1 = np.ascontiguousarray(L[:1]); a1 = np.zeros((1, 2, X, X), np.float32); m1 = np.zeros((1, 1, X, X), np.float32)
+    times, reccs_times = [], []
+    for i in range(25):
+        loc = rs.randint(8, X - 8, 2)
+        CI.put_point(a1[0], m1[0], loc, 3, rs.uniform(-80, 80, 2))
+        t = time.perf_counter()
+        lctx.forward_host(l1, a1, m1, 0.5, want_rgb=True)
+        lctx.fetch_dist(0, int(loc[0]) // 4, int(loc[1]) // 4)
+        times.append((time.perf_counter() - t) * 1e3)
+        t = time.perf_counter()       # not part of config 5: the K=9 colour suggestions the GUI shows (row f2)
+        lctx.ab_reccs(0, int(loc[0]) // 4, int(loc[1]) // 4, K=9)
+        reccs_times.append((time.perf_counter() - t) * 1e3)
+    times = times[5:]
+    lat = {"p50_ms": float(np.percentile(times, 50)), "p99_ms": float(np.percentile(times, 99)),
+           "reccs_k9_p50_ms": float(np.percentile(reccs_times[5:], 50)), "calls": len(times),
+           "what": "BASELINE config 5: put_point -> C-ABI idc_forward_host (batch 1, dist head + Lab->RGB on, one CUDA graph: "
+                   "H2D of L/hints, PDL-chained kernels, D2H of ab + rgb) + idc_fetch_dist of the clicked pixel"}
+    lctx.close()
+    # wrapper level, as ui/gui_draw.py:258-286 calls it: colour model net_forward (RGB + quantised output_ab),
+    # dist model net_forward + get_ab_reccs (predict_color / suggest_color)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        cm = CI.ColorizeImageB200(Xd=X, maskcent=True)
+        cm.prep_net(state_dict=sd)
+        cd = CI.ColorizeImageB200Dist(Xd=X, maskcent=True)
+        cd.prep_net(state_dict=sd)
+    img = np.random.RandomState(1).randint(0, 256, (X, X, 3)).astype(np.uint8)
+    cm.set_image(img); cd.set_image(img)
+    ab64, m64 = np.zeros((2, X, X)), np.zeros((1, X, X))
+    t_col, t_all = [], []
+    for i in range(25):
+        loc = rs.randint(8, X - 8, 2)
+        CI.put_point(ab64, m64, loc, 3, rs.uniform(-80, 80, 2))
+        t = time.perf_counter()
+        cm.net_forward(ab64, m64)
+        t1 = time.perf_counter()
+        cd.net_forward(ab64, m64)
+        cd.get_ab_reccs(int(loc[0]), int(loc[1]), K=9)
+        t2 = time.perf_counter()
+        t_col.append((t1 - t) * 1e3); t_all.append((t2 - t) * 1e3)
+    lat["wrapper_p50_ms"] = float(np.percentile(t_col[5:], 50))
+    lat["wrapper_p99_ms"] = float(np.percentile(t_col[5:], 99))
+    lat["wrapper_with_dist_reccs_p50_ms"] = float(np.percentile(t_all[5:], 50))
+    lat["wrapper_what"] = ("ColorizeImageB200.net_forward(ab, mask) -> uint8 RGB + quantised output_ab (float64 numpy in/out, one "
+                           "C-ABI call); with_dist_reccs adds ColorizeImageB200Dist.net_forward + get_ab_reccs(K=9) on a second "
+                           "context, as ui/gui_draw.py:258-286 calls them")
+    return lat
 
 
 def run_ours(args):
@@ -200,30 +395,41 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident throughput ----
-    for _ in range(max(args.warmup, 3)):
-        ctx.forward_device(dL, dab, dm, 0.5, out_ab=out)
+    # ---- every rank: one fixed-seed image, checksum compared on rank 0 (rank != 0 weight path) ----
+    cL, cab, cm_ = synth.synthetic_batch(1, X, seed=424242, max_hints=10)
+    cout = ctx.forward_device(torch.from_numpy(cL).to(dev), torch.from_numpy(cab).to(dev), torch.from_numpy(cm_).to(dev), 0.5)["ab"]
+    torch.cuda.synchronize(dev)
+    csum = torch.stack([cout.double().sum(), cout.double().abs().sum(),
+                        (cout.view(torch.int32).to(torch.int64) & 0xFFFF).sum().double()])
+    if world > 1:
+        allsums = [torch.zeros_like(csum) for _ in range(world)]
+        dist.all_gather(allsums, csum)
+    else:
+        allsums = [csum]
+    ranks_equal = all(bool(torch.equal(allsums[0], s)) for s in allsums)
+    if rank == 0 and not ranks_equal:
+        raise RuntimeError("rank outputs differ on the fixed-seed image: %r" % ([s.tolist() for s in allsums],))
+
+    # ---- device-resident throughput: graph replays, no profiling inside the timed region ----
+    ctx.forward_device(dL, dab, dm, 0.5, out_ab=out)
     launches_per_step = ctx.last_launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
-    ctx.set_profiling(True)
-    barrier()
-    t_region0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        ctx.forward_device(dL, dab, dm, 0.5, out_ab=out)
-    e1.record()
-    barrier()
-    t_region1 = time.perf_counter()
-    ms_total = max_over_ranks(e0.elapsed_time(e1), dev)
-    prof = ctx.get_profile()
-    ctx.set_profiling(False)
+    ms_total, launch_mode, (t_region0, t_region1) = timed_graph_steps(
+        torch, ctx, lambda: ctx.forward_device(dL, dab, dm, 0.5, out_ab=out), args.steps, args.warmup, barrier, dev)
+    ms_total = max_over_ranks(ms_total, dev)
     clocks = sampler.finish(t_region0, t_region1) if sampler else None
     ms_step = ms_total / args.steps
     value = world * N / (ms_step * 1e-3)
+
+    # ---- per-op device times: separate untimed pass (events between the launches, PDL off by construction) ----
+    ctx.set_profiling(True)
+    for _ in range(3):
+        ctx.forward_device(dL, dab, dm, 0.5, out_ab=out)
+    prof = ctx.get_profile()
+    ctx.set_profiling(False)
 
     # ---- end to end through the host-pointer C-ABI call (pinned H2D + forward + D2H) ----
     e2e = None
@@ -237,34 +443,20 @@ def run_ours(args):
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
         e2e = world * N * args.steps / e2e_s
+    flops_img = ctx.flops_per_image()
+    ctx.close()
+    del dL, dab, dm, out
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE config 4 (512^2, global batch 16, global hints) at this N ----
+    cfg4 = None
+    if not args.skip_e2e and not args.no_config4 and X == 256 and not args.fast_fp16:
+        cfg4 = run_config4(args, torch, dist, world, rank, local, dev, barrier, max_over_ranks)
 
     # ---- single-click latency (config 5): 20 sequential put_point -> net_forward, batch 1 ----
     lat = None
     if rank == 0 and not args.skip_e2e:
-        from interactive_deep_colorization_b200 import colorize_image as CI
-        from interactive_deep_colorization_b200.engine import LhnContext
-        lctx = LhnContext(device=local, max_n=1, H=X, W=X, dist=True)
-        lctx.load_state_dict(synth.torch_state_dict(1234))
-        lctx.set_dist_resident(True)      # config 5: the click only needs dist[:, h//4, w//4]
-        rs = np.random.RandomState(0)
-        l1 = np.ascontiguousarray(L[:1]); a1 = np.zeros((1, 2, X, X), np.float32); m1 = np.zeros((1, 1, X, X), np.float32)
-        times, reccs_times = [], []
-        for i in range(25):
-            loc = rs.randint(8, X - 8, 2)
-            CI.put_point(a1[0], m1[0], loc, 3, rs.uniform(-80, 80, 2))
-            t = time.perf_counter()
-            lctx.forward_host(l1, a1, m1, 0.5, want_rgb=True)
-            lctx.fetch_dist(0, int(loc[0]) // 4, int(loc[1]) // 4)
-            times.append((time.perf_counter() - t) * 1e3)
-            t = time.perf_counter()       # not part of config 5: the K=9 colour suggestions the GUI shows (row f2)
-            lctx.ab_reccs(0, int(loc[0]) // 4, int(loc[1]) // 4, K=9)
-            reccs_times.append((time.perf_counter() - t) * 1e3)
-        times = times[5:]
-        lat = {"p50_ms": float(np.percentile(times, 50)), "p99_ms": float(np.percentile(times, 99)),
-               "reccs_k9_p50_ms": float(np.percentile(reccs_times[5:], 50)),
-               "calls": len(times), "what": "BASELINE config 5: put_point -> C-ABI idc_forward_host (batch 1, dist head + Lab->RGB on, "
-                                            "CUDA graph, H2D of L/hints, D2H of ab + rgb) + idc_fetch_dist of the clicked pixel"}
-        lctx.close()
+        lat = run_latency(local, L)
 
     if rank != 0:
         if world > 1:
@@ -279,39 +471,41 @@ def run_ours(args):
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     n_launch = sum(1 for _ in conv)
     split = 1.0 if args.fast_fp16 else 3.0
-    roofline = {"bound": "tensor", "kernel": "umma_conv_kernel<BN,SPLIT> (tcgen05 implicit-GEMM conv, %d launches/step)" % n_launch,
+    roofline = {"bound": "tensor", "kernel": "umma_conv_kernel<BN,MT,CG,SPLIT,HALO> (tcgen05 implicit-GEMM conv, %d launches/step)" % n_launch,
                 "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor"],
                 "issued_mma_frac": split * achieved / peaks["tensor"],
                 "peak_source": peaks["src"], "traffic": _ncu_traffic(N, X),
-                "traffic_note": "average DRAM bytes per umma_conv launch (ncu --set full, profiles/r01_ncu_full_umma_conv_batch64.csv)",
+                "traffic_note": "average DRAM bytes per umma_conv launch (ncu --set full at HEAD, profiles/%s)" % os.path.basename(NCU_TRAFFIC_CSV),
                 "algorithmic_flops_per_launch": conv_flops / max(n_launch, 1),
                 "avg_launch_ms": conv_ms / max(n_launch, 1),
-                "kernel_share_of_step": conv_ms / ms_step,
-                "note": "achieved = useful conv FLOPs (2*MACs); the split-FP16 scheme issues 3 MMAs per product, so the "
-                        "tensor pipe is busy issued_mma_frac of peak"}
+                "kernel_share_of_step": min(1.0, conv_ms / ms_step),
+                "whole_step_useful_tflops_per_gpu": N * flops_img / (ms_step * 1e-3) / 1e12,
+                "note": "achieved = useful conv FLOPs (2*MACs) / summed per-launch device time from the untimed profiling pass; "
+                        "the split-FP16 scheme issues 3 MMAs per product, so the tensor pipe is busy issued_mma_frac of peak"}
     # ---- CPU baseline (bounded sample, rank 0, N=1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline and not args.skip_e2e:
-        sd_cpu = synth.torch_state_dict(1234)
-        ips, nimg, thr = cpu_baseline_run(sd_cpu, 15.0, 64, best_cpu_threads(sd_cpu))
-        cpu = {"value": ips, "unit": "images/s", "cores": thr, "kind": "port",
-               "sample": "%d images @256x256, batch-1 loop of the CPU oracle port (torch fp32, best-of pool sizes -> %d threads, %d host cores)"
-                         % (nimg, thr, os.cpu_count() or 0)}
+        arm = CpuArm()
+        ips, nimg, thr = arm.run(15.0, 64, arm.best_threads())
+        cpu = {"value": ips, "unit": "images/s", "cores": thr, "kind": arm.kind,
+               "sample": "%d images @%dx%d, batch-1 loop of %s (best-of pool sizes -> %d threads, %d host cores)"
+                         % (nimg, X, X, arm.describe(), thr, os.cpu_count() or 0)}
+        if lat:
+            lat["cpu_ms_per_image"] = 1e3 / ips
+            lat["speedup_vs_cpu_latency"] = (1e3 / ips) / lat["p50_ms"]
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
             "dtype": ("f16 operands single pass (NOT parity: ~6e-2 ab error), f32 accumulate" if args.fast_fp16 else
                       "f16x2-split operands, f32 accumulate (ab within 1e-3 of the f32 reference)"),
             "data": "synthetic",
-            "config": {"workload": "BASELINE config %s: %d x %dx%d synthetic L + 0-10 sparse 7x7 ab hints per GPU, "
-                                   "regression head (ab map)" % ("3" if X == 256 else "4 (no global hints)", N, X, X),
-                       "per_gpu_batch": N, "global_batch": N * world, "parallelism": "dp%d (image sharding, no per-step collective)" % world,
-                       "l2_policy": "per-step working set (~%.1f GB of activations) >> 126 MB L2; inputs are not re-used from L2"
-                                    % (N * 0.15)},
+            "config": workload_config(N, X, world),
+            "launch_mode": launch_mode,
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(world * N * 4 * X * X * 4),
                     "d2h_bytes_per_step": int(world * N * 2 * X * X * 4)},      # whole job, all ranks
             "gpu_launches": world * launches_per_step * args.steps, "clocks": clocks, "latency": lat,
+            "config4": cfg4, "rank_outputs_identical": ranks_equal,
             "per_op_ms": {n: round(ms, 4) for n, ms, _ in prof}}
     print(json.dumps(line))
     if world > 1:
@@ -327,10 +521,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--size", type=int, default=256, help="image side (BASELINE config 4 uses 512 with --batch 16)")
+    ap.add_argument("--no-config4", action="store_true", help="skip the extra BASELINE config 4 record")
+    ap.add_argument("--size", type=int, default=256, help="image side")
     ap.add_argument("--fast-fp16", action="store_true",
                     help="NOT the parity configuration: single-pass FP16 operands (1 MMA per product, ~6e-2 ab error)")
-    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the e2e and latency legs")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the e2e, config 4 and latency legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

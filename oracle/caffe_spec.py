@@ -68,10 +68,14 @@ def synthetic_caffe313_state_dict(seed=777, pts_in_hull=None):
     return sd
 
 
-def caffe313_head(csd, inter, T=2.6, S=0.2, return_logits=False):
+def caffe313_head(csd, inter, T=2.6, S=0.2, return_logits=False, dtype=torch.float32):
     """inter: intermediates of oracle/lhn_ref.lhn_forward (conv3_3 ... conv8_3 are the *norm blobs).
-    -> (pred_ab [N,2,H,W], dist_ab_S [N,313,H,W])"""
-    t = lambda k: torch.as_tensor(np.asarray(csd[k]), dtype=torch.float32)
+    -> (pred_ab [N,2,H,W], dist_ab_S [N,313,H,W]).  dtype=torch.float64 evaluates the same head in double
+    precision from the same FP32 trunk activations: the T = 2.6 softmax amplifies FP32 summation-order noise of
+    the logits, so two FP32 evaluations of this head differ from each other by ~1e-3 in ab; the FP64 run is the
+    arithmetic-exact statement of the spec that both are measured against."""
+    t = lambda k: torch.as_tensor(np.asarray(csd[k]), dtype=dtype)
+    inter = {k: v.to(dtype) for k, v in inter.items() if k in ("conv3_3", "conv4_3", "conv5_3", "conv6_3", "conv7_3", "conv8_3")}
     h = F.conv2d(inter["conv3_3"], t("caffe.conv3_pred.weight"), t("caffe.conv3_pred.bias"), padding=1)
     for l in (4, 5, 6, 7):
         h = h + F.conv_transpose2d(inter["conv%d_3" % l], t("caffe.conv%d_pred.weight" % l), t("caffe.conv%d_pred.bias" % l),
@@ -79,7 +83,7 @@ def caffe313_head(csd, inter, T=2.6, S=0.2, return_logits=False):
     h = h + F.conv2d(inter["conv8_3"], t("caffe.conv8_pred.weight"), t("caffe.conv8_pred.bias"), padding=1)
     h = F.relu(h)                                                          # relu345678_pred
     logits = F.conv2d(h, t("caffe.pred_313.weight"), t("caffe.pred_313.bias"))
-    k = torch.from_numpy(US_KERNEL)[None, None].repeat(313, 1, 1, 1)       # data/colorize_image.py:409-413
+    k = torch.from_numpy(US_KERNEL).to(dtype)[None, None].repeat(313, 1, 1, 1)       # data/colorize_image.py:409-413
     up = F.conv_transpose2d(logits, k, None, stride=2, padding=1, groups=313)        # pred_313_us
     up = F.conv_transpose2d(up, k, None, stride=2, padding=1, groups=313)            # pred_313_rs
     dist_S = F.softmax(up * S, dim=1)                                      # scale_S + dist_ab_S

@@ -196,7 +196,9 @@ def test_caffe313_head(synth_sd):
     _, inter = util.oracle_forward(synth_sd, L, ab, m, 0.5, intermediates=True)
     with torch.no_grad():
         pred_ref, distS_ref, logits_ref, hyper_ref = caffe_spec.caffe313_head(csd, inter, return_logits=True)
+        pred64, _, logits64, _ = caffe_spec.caffe313_head(csd, inter, return_logits=True, dtype=torch.float64)
     assert float(pred_ref.abs().max()) > 5.0
+    ref32_vs_64 = util.maxabs(pred_ref, pred64)            # how far an FP32 evaluation of the spec is from exact arithmetic
     for engine in ("simt", "tcgen05"):
         ctx = util.make_ctx(sd, 64, 64, max_n=2, engine=engine, caffe313=True)
         ctx.forward_device(util.dev(L), util.dev(ab), util.dev(m), 0.5)
@@ -204,11 +206,18 @@ def test_caffe313_head(synth_sd):
         assert util.maxabs(ctx.get_activation("hyper", 2), hyper_ref) < 3e-4, engine
         pred = ctx.caffe313_pred_ab(2)
         torch.cuda.synchronize()
-        err = util.maxabs(pred, pred_ref)
-        print("caffe313 %s: max|d pred_ab| = %.3e" % (engine, err))
-        # spec-only head, parity unpinned: the T=2.6 softmax amplifies FP32 ordering noise of the logits
-        # (the exact-FP32 SIMT engine itself sits at 8.7e-4 from the CPU oracle), so 3e-3 on |ab| <= 100
-        assert err <= 3e-3, (engine, err)
+        err, err64 = util.maxabs(pred, pred_ref), util.maxabs(pred, pred64)
+        d = (pred.cpu().double() - pred64).abs()
+        w = int(d.argmax())
+        n_, c_, y_, x_ = np.unravel_index(w, tuple(d.shape))
+        top2 = torch.topk(logits64[n_, :, y_ // 4, x_ // 4], 2).values
+        print("caffe313 %s: max|d pred_ab| vs FP32 oracle %.3e, vs FP64 evaluation %.3e (FP32 oracle vs FP64: %.3e); worst pixel "
+              "(n=%d, c=%d, y=%d, x=%d), top-2 logit gap there %.3f (x T=2.6 in the softmax)"
+              % (engine, err, err64, ref32_vs_64, n_, c_, y_, x_, float(top2[0] - top2[1])))
+        # spec-only head (parity unpinned).  The bar is the north_star's 1e-3, measured against the FP64 evaluation
+        # of the spec; where the FP32 oracle itself is further than that from exact arithmetic (the annealed-mean
+        # softmax multiplies logit noise by T * |ab range|), twice the oracle's own distance is allowed.
+        assert err64 <= max(1e-3, 2.0 * ref32_vs_64), (engine, err64, ref32_vs_64)
         for (y, x) in ((0, 0), (13, 62), (63, 63), (31, 7)):
             d = ctx.caffe313_dist_pixel(1, y, x)
             assert util.maxabs(d, distS_ref[1, :, y, x]) < 1e-5, (engine, y, x)
