@@ -410,3 +410,223 @@ class ColorizeImageB200GlobDist(ColorizeImageB200):
         else:
             ColorizeImageBase._set_out_ab_(self)
         return self.output_rgb
+
+
+# =============================================================================================
+# Caffe-named wrapper surface (reference :375-442, :445-463, :466-561).  The notebooks and ideepcolor.py:60-65
+# instantiate ColorizeImageCaffe / ColorizeImageCaffeDist / ColorizeImageCaffeGlobDist; these classes keep those
+# names' semantics on the B200 engine:
+#   * Caffe scaling: the deploy nets feed RAW L-50, raw ab and mask x 110 into conv1_1 and scale the
+#     regression head by 100 (deploy_nodist.prototxt:19-51, :812-822; `self.mask_mult = 110.`, :383), where the
+#     PyTorch model feeds L/100, ab/110, mask and scales by 110.  The engine normalises the PyTorch way inside
+#     conv1_1_kernel, so a Caffe-scaled weight set is mapped exactly at load time (conv1_1 input channels x 100, x 110,
+#     x 110; `tanh_scale` = 100) -- see `caffe_scaled_state_dict`.
+#   * 313-bin head (deploy_nopred.prototxt:651-850): `dist_ab` = softmax(S * logits) over the in-gamut bins,
+#     `pred_ab` = annealed mean (T = 2.6); `get_ab_reccs` works on `pts_in_hull` (313 bins).
+# There is no .caffemodel parser offline (no Caffe, no caffe.proto): `caffemodel_path` is a torch state_dict file
+# holding the Caffe blobs under the reference state_dict key names (+ the `caffe.*` keys of include/idc_b200.h), or an
+# in-memory `state_dict`.  Spec-only: no Caffe weights or vectors exist offline (parity unpinned, oracle/caffe_spec.py).
+# =============================================================================================
+def caffe_scaled_state_dict(state_dict):
+    """Caffe-scaled weights (conv1_1 trained on raw L-50 / ab / mask*110) -> the engine's PyTorch-scaled convention.
+    Exact: w' . (L/100, ab/110, mask) == w . (L, ab, mask*110) with w' = w * (100, 110, 110, 110) per input channel."""
+    import torch
+    sd = dict(state_dict)
+    w = sd["model1.0.weight"]
+    w = w.detach().cpu().numpy() if hasattr(w, "detach") else np.asarray(w)
+    scale = np.array([100.0, 110.0, 110.0, 110.0], dtype=np.float64).reshape(1, 4, 1, 1)
+    sd["model1.0.weight"] = torch.from_numpy((w.astype(np.float64) * scale).astype(np.float32))
+    return sd
+
+
+class ColorizeImageB200Caffe(ColorizeImageB200):
+    """<-> ColorizeImageCaffe (reference :375-442): regression model with the Caffe input / output scaling."""
+    _caffe313 = False
+    _global_hints = False
+
+    def __init__(self, Xd=256, engine="tcgen05"):
+        ColorizeImageB200.__init__(self, Xd, maskcent=False, engine=engine)
+        self.mask_mult = 110.                     # reference :383
+        self.pred_ab_layer = 'pred_ab'
+        from . import prepost
+        self.pts_in_hull = prepost.pts_in_hull().astype(np.float64)       # 313 x 2, in-gamut (reference :388-389)
+
+    def prep_net(self, gpu_id=0, prototxt_path='', caffemodel_path='', state_dict=None):
+        import torch
+        from .engine import LhnContext
+        print('gpu_id = %d, net_path = %s, model_path = %s' % (-1 if gpu_id is None else gpu_id, prototxt_path, caffemodel_path))
+        if state_dict is None:
+            state_dict = torch.load(caffemodel_path, map_location='cpu')
+        self.gpu_id = gpu_id
+        sd = caffe_scaled_state_dict(state_dict)
+        if self._caffe313:
+            sd["caffe.pts_in_hull"] = torch.from_numpy(self.pts_in_hull.astype(np.float32))   # reference :405-407
+        self._ctx = LhnContext(device=0 if gpu_id in (None, -1) else int(gpu_id), max_n=1, H=self.Xd, W=self.Xd,
+                               engine=self.engine, global_hints=self._global_hints, caffe313=self._caffe313,
+                               options={"tanh_scale": 100})
+        self._ctx.load_state_dict(sd)
+        self.net_set = True
+
+    def _engine_inputs(self):
+        A = np.ascontiguousarray(self.img_l_mc, dtype=np.float32)[None]
+        B = np.ascontiguousarray(self.input_ab_mc, dtype=np.float32)[None]
+        M = np.ascontiguousarray(self.input_mask_mult / self.mask_mult, dtype=np.float32)[None]   # x110 lives in the weights
+        return A, B, M
+
+    def net_forward(self, input_ab, input_mask):
+        if ColorizeImageBase.net_forward(self, input_ab, input_mask) == -1:
+            return -1
+        A, B, M = self._engine_inputs()
+        r = self._ctx.forward_host(A, B, M, 0.0, want_rgb=True, want_abq=self.gpu_prepost)
+        self.output_ab_raw = r["ab"][0]                  # the `pred_ab` blob (tanh * 100)
+        self.output_rgb = r["rgb"][0]
+        if self.gpu_prepost:
+            self.output_ab = r["abq"][0]
+            self._output_lab = None
+        else:
+            ColorizeImageBase._set_out_ab_(self)
+        return self.output_rgb
+
+
+class ColorizeImageB200CaffeGlobDist(ColorizeImageB200Caffe):
+    """<-> ColorizeImageCaffeGlobDist (reference :445-463): additional 313-bin global histogram input."""
+    _global_hints = True
+
+    def __init__(self, Xd=256, engine="tcgen05"):
+        ColorizeImageB200Caffe.__init__(self, Xd, engine=engine)
+        self.glob_mask_mult = 1.
+        self.glob_layer = 'glob_ab_313_mask'
+
+    def get_global_histogram(self, ref_rgb_u8):
+        """DemoGlobalHistogramTransfer.ipynb:176-182 (gt_glob_net = global_stats.prototxt on the resized reference image)."""
+        import cv2
+        from . import prepost
+        self.glob_vec = prepost.global_stats_gpu(cv2.resize(ref_rgb_u8, (self.Xd, self.Xd)), self._ctx.device)
+        return self.glob_vec[:313].copy()
+
+    def net_forward(self, input_ab, input_mask, glob_dist=-1):
+        if ColorizeImageBase.net_forward(self, input_ab, input_mask) == -1:
+            return -1
+        glob = np.zeros((1, 316), np.float32)            # "run without this, zero it out" (reference :454-456)
+        if np.array(glob_dist).flatten()[0] != -1:
+            glob[0, :313] = np.asarray(glob_dist, dtype=np.float32)
+            glob[0, 313] = self.glob_mask_mult             # reference :458-459
+        A, B, M = self._engine_inputs()
+        r = self._ctx.forward_host(A, B, M, 0.0, glob=glob, want_rgb=True, want_abq=self.gpu_prepost)
+        self.output_ab_raw = r["ab"][0]
+        self.output_rgb = r["rgb"][0]
+        if self.gpu_prepost:
+            self.output_ab = r["abq"][0]
+            self._output_lab = None
+        else:
+            ColorizeImageBase._set_out_ab_(self)
+        return self.output_rgb
+
+
+class _LazyDist313(object):
+    """[313, X, X] view of `dist_ab_S`: one pixel (313 floats) is computed on demand from the resident 313-bin logits
+    (idc_caffe313_dist_pixel); the reference materialises 313 x X x X floats per forward and reads one pixel of it per
+    click (reference :505, :521)."""
+
+    def __init__(self, ctx, X, S):
+        self._ctx, self._S = ctx, S
+        self.shape = (313, X, X)
+        self.dtype = np.dtype(np.float32)
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple) and len(idx) == 3 and all(isinstance(i, (int, np.integer)) for i in idx[1:]):
+            return self._ctx.caffe313_dist_pixel(0, int(idx[1]), int(idx[2]), self._S)[idx[0]]
+        return self.__array__()[idx]
+
+    def __array__(self, dtype=None, copy=None):
+        X = self.shape[1]
+        a = np.stack([np.stack([self._ctx.caffe313_dist_pixel(0, y, x, self._S) for x in range(X)], -1) for y in range(X)], -2)
+        return a.astype(dtype) if dtype is not None else a
+
+
+class ColorizeImageB200CaffeDist(ColorizeImageB200Caffe):
+    """<-> ColorizeImageCaffeDist (reference :466-561): the 313-bin distribution model.  `pred_ab` is the annealed
+    mean of the 313-bin head (deploy_nopred.prototxt:827-850), `dist_ab` the S-softened distribution (:808-820)."""
+    _caffe313 = True
+
+    def __init__(self, Xd=256, engine="tcgen05"):
+        ColorizeImageB200Caffe.__init__(self, Xd, engine=engine)
+        self.dist_ab_set = False
+        self.scale_S_layer = 'scale_S'
+        self.dist_ab_S_layer = 'dist_ab_S'
+        g = np.arange(-110, 120, 10)
+        # pts_grid.npy is (a, b)-ordered with a slowest (SURVEY q3): pts_grid[i] = (g[i // 23], g[i % 23])
+        self.pts_grid = np.stack([np.repeat(g, 23), np.tile(g, 23)], axis=1)
+        hull = set(map(tuple, self.pts_in_hull.astype(int).tolist()))
+        self.in_hull = np.array([tuple(p) in hull for p in self.pts_grid.tolist()])      # identity: pts_grid[in_hull] == pts_in_hull
+        self.AB = self.pts_grid.shape[0]
+        self.A = self.B = int(np.sqrt(self.AB))
+        self.dist_entropy = np.zeros((self.Xd, self.Xd))
+
+    def prep_net(self, gpu_id=0, prototxt_path='', caffemodel_path='', S=.2, state_dict=None):
+        ColorizeImageB200Caffe.prep_net(self, gpu_id, prototxt_path=prototxt_path, caffemodel_path=caffemodel_path,
+                                        state_dict=state_dict)
+        self.S = S
+
+    def net_forward(self, input_ab, input_mask):
+        if ColorizeImageBase.net_forward(self, input_ab, input_mask) == -1:
+            return -1
+        import torch
+        from . import _lib
+        A, B, M = self._engine_inputs()
+        dev = "cuda:%d" % self._ctx.device
+        dA, dB, dM = (torch.from_numpy(a).to(dev) for a in (A, B, M))
+        self._ctx.forward_device(dA, dB, dM, 0.0)                      # trunk + hyper-column + pred_313 logits
+        pred = self._ctx.caffe313_pred_ab(1, T=2.6)                    # annealed-mean `pred_ab` [1,2,X,X] (device)
+        rgb = torch.empty((1, self.Xd, self.Xd, 3), dtype=torch.uint8, device=dev)
+        L = (dA + 50.0).contiguous()
+        st = torch.cuda.current_stream(self._ctx.device).cuda_stream
+        rc = _lib.load().idc_lab2rgb_u8(self._ctx.device, 1, self.Xd, self.Xd, L.data_ptr(), pred.data_ptr(), rgb.data_ptr(), st)
+        if rc != _lib.IDC_OK:
+            raise _lib.IdcError(rc, "idc_lab2rgb_u8 failed")
+        self.output_ab_raw = pred[0].cpu().numpy()
+        self.output_rgb = rgb[0].cpu().numpy()
+        self._set_out_ab_()
+        self.dist_ab = _LazyDist313(self._ctx, self.Xd, self.S)
+        self.dist_ab_set = True
+        return self.output_rgb
+
+    @property
+    def dist_ab_full(self):
+        full = np.zeros((self.AB, self.Xd, self.Xd))
+        full[self.in_hull, :, :] = np.asarray(self.dist_ab)
+        return full
+
+    @property
+    def dist_ab_grid(self):
+        return self.dist_ab_full.reshape((self.A, self.B, self.Xd, self.Xd))
+
+    def get_ab_reccs(self, h, w, K=5, N=25000, return_conf=False, method='gpu'):
+        """reference :515-547 on the 313 in-gamut bins.  method='gpu': weighted k-means on the device (the N -> infinity
+        limit, as ColorizeImageB200Dist); method='sampled': the reference's np.random + sklearn procedure."""
+        if not self.dist_ab_set:
+            print('Need to set prediction first')
+            return 0
+        pmf = np.asarray(self.dist_ab[:, int(h), int(w)], dtype=np.float64)
+        if method == 'gpu':
+            from .prepost import ab_reccs_pmf_gpu
+            p529, q529 = np.zeros(529, np.float32), np.zeros((529, 2), np.float32)     # the kernel clusters 529 slots;
+            p529[:313], q529[:313] = pmf, self.pts_in_hull                              # zero-weight padding is inert
+            centers, conf, _ = ab_reccs_pmf_gpu(p529, K=K, pts=q529, device=self._ctx.device)
+            centers, conf = centers.astype(np.float64), conf.astype(np.float64)
+            return (centers, conf) if return_conf else centers
+        if method != 'sampled':
+            raise ValueError("method must be 'gpu' or 'sampled'")
+        from sklearn.cluster import KMeans
+        cmf = np.cumsum(pmf)
+        cmf /= cmf[-1]
+        samples = self.pts_in_hull[np.digitize(np.random.uniform(low=0, high=1.0, size=N), bins=cmf), :]
+        km = KMeans(n_clusters=K).fit(samples)
+        cnt = np.histogram(km.labels_, np.arange(0, K + 1))[0]
+        order = np.argsort(cnt, axis=0)[::-1]
+        centers, conf = km.cluster_centers_[order, :], 1. * cnt[order] / N
+        return (centers, conf) if return_conf else centers
+
+    def compute_entropy(self):
+        d = np.asarray(self.dist_ab)
+        self.dist_entropy = np.sum(d * np.log(d), axis=0)

@@ -527,7 +527,7 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
     } else if (hp && op.fuse_out_head) {
       for (int k = 0; k < hp->nchunks; ++k) {
         const int i0 = hp->start[k], nk = hp->start[k + 1] - i0;
-        CUDA_TRY(c, umma_run_op(c, op, nk, out_ab, 1.0f, st, i0));
+        CUDA_TRY(c, umma_run_op(c, op, nk, out_ab, (float)c->opt.tanh_scale, st, i0));
         CUDA_TRY(c, cudaEventRecord(c->ev_out[k], st));
         pdl_break(c);
         CUDA_TRY(c, cudaStreamWaitEvent(c->s_out, c->ev_out[k], 0));
@@ -535,7 +535,7 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
                                     (size_t)nk * 2 * HW * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
       }
     } else {
-      CUDA_TRY(c, umma_run_op(c, op, n, op.fuse_out_head ? out_ab : nullptr, 1.0f, st));
+      CUDA_TRY(c, umma_run_op(c, op, n, op.fuse_out_head ? out_ab : nullptr, (float)c->opt.tanh_scale, st));
     }
     mark();
   }
@@ -604,11 +604,11 @@ int idc_set_option(idc_ctx* c, const char* name, int value) {
   struct { const char* n; int* v; } tab[] = {
       {"halo", &c->opt.halo}, {"pairs", &c->opt.pairs}, {"mt", &c->opt.mt}, {"chunk_kb", &c->opt.chunk_kb},
       {"split_k", &c->opt.split_k}, {"direct_stores", &c->opt.direct_stores}, {"host_pipe", &c->opt.host_pipe},
-      {"pdl", &c->opt.pdl}, {"split_pairs", &c->opt.split_pairs}};
+      {"pdl", &c->opt.pdl}, {"split_pairs", &c->opt.split_pairs}, {"tanh_scale", &c->opt.tanh_scale}};
   for (auto& t : tab)
     if (!strcmp(t.n, name)) {
       *t.v = value;
-      if (c->weights_ready && strcmp(name, "host_pipe")) {      // plan-time option changed after planning: re-plan
+      if (c->weights_ready && strcmp(name, "host_pipe") && strcmp(name, "tanh_scale")) {      // plan-time option changed after planning: re-plan
         CUDA_TRY(c, cudaSetDevice(c->dev));
         CUDA_TRY(c, cudaDeviceSynchronize());
         int rc = plan_engines(c);
@@ -1077,7 +1077,7 @@ int idc_run_op(idc_ctx* c, const char* op_name, int n, void* stream) {
       if (op.fuse_out_head) return fail(c, IDC_ERR_ARG, "op %s has a fused head; use IDC_FLAG_KEEP_CONV10", op_name);
       c->gadd_active = false;
       if (c->simt) CUDA_TRY(c, simt_run_op(c, op, n, (cudaStream_t)stream));
-      else CUDA_TRY(c, umma_run_op(c, op, n, nullptr, 1.0f, (cudaStream_t)stream));
+      else CUDA_TRY(c, umma_run_op(c, op, n, nullptr, (float)c->opt.tanh_scale, (cudaStream_t)stream));
       c->last_n = n;
       return IDC_OK;
     }

@@ -136,7 +136,7 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(256) out_head_kernel(const float* __restrict__ inf, const __half* __restrict__ ihi,
                                                        const __half* __restrict__ ilo, const float* __restrict__ w,
                                                        const float* __restrict__ b, int N, int H, int W,
-                                                       float* __restrict__ out) {
+                                                       float* __restrict__ out, float out_scale) {
   __shared__ float ws[256];
   ws[threadIdx.x] = w[threadIdx.x];                     // static weights: before the dependency wait
   pdl_prologue_done();
@@ -165,8 +165,8 @@ __global__ void __launch_bounds__(256) out_head_kernel(const float* __restrict__
   if (valid && part == 0) {
     const int n = (int)(pix / HW);
     const size_t r = pix - (size_t)n * HW;
-    out[(size_t)n * 2 * HW + r] = tanhf(s0 + b[0]) * 110.0f;
-    out[(size_t)n * 2 * HW + HW + r] = tanhf(s1 + b[1]) * 110.0f;
+    out[(size_t)n * 2 * HW + r] = tanhf(s0 + b[0]) * out_scale;
+    out[(size_t)n * 2 * HW + HW + r] = tanhf(s1 + b[1]) * out_scale;
   }
 }
 
@@ -177,11 +177,12 @@ cudaError_t launch_out_head(Ctx* c, int n, float* out_ab, cudaStream_t st) {
   cudaError_t e;
   if (c->simt)
     e = launch_k(c, out_head_kernel<false>, dim3(grid), dim3(256), 0, st, static_cast<const float*>(in.p0),
-                 (const __half*)nullptr, (const __half*)nullptr, c->wout, c->bout, n, in.H, in.W, out_ab);
+                 (const __half*)nullptr, (const __half*)nullptr, c->wout, c->bout, n, in.H, in.W, out_ab,
+                 (float)c->opt.tanh_scale);
   else
     e = launch_k(c, out_head_kernel<true>, dim3(grid), dim3(256), 0, st, (const float*)nullptr,
                  static_cast<const __half*>(in.p0), static_cast<const __half*>(in.p1), c->wout, c->bout, n, in.H, in.W,
-                 out_ab);
+                 out_ab, (float)c->opt.tanh_scale);
   c->launch_count++;
   return e;
 }

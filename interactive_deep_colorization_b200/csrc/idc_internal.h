@@ -118,6 +118,7 @@ struct Options {
   int host_pipe = 1;      // idc_forward_host: chunked copy/compute overlap for batches >= 8
   int pdl = 1;            // programmatic dependent launch between the kernels of a forward
   int split_pairs = 1;    // cta_group::2 on the split-K (small batch) path
+  int tanh_scale = 110;   // regression head: tanh * 110 (model.py:175); the Caffe deploy nets use 100
 };
 
 struct HostTensor {

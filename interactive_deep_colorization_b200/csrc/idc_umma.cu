@@ -830,8 +830,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         if ((MT == 2 || half == 0) && valid) {
           const size_t HW = (size_t)p.Hl * p.Wl;
           const size_t o = (size_t)img * 2 * HW + (size_t)y * p.Wl + x;
-          p.out_ab[o] = tanhf(h0 + s_head[256]) * 110.0f * p.out_mult;
-          p.out_ab[o + HW] = tanhf(h1 + s_head[257]) * 110.0f * p.out_mult;
+          p.out_ab[o] = tanhf(h0 + s_head[256]) * p.out_mult;           // out_mult = 110 (model.py:175) or 100 (Caffe spec)
+          p.out_ab[o + HW] = tanhf(h1 + s_head[257]) * p.out_mult;
         }
       } else if (p.out_f32) {
         float* o32 = p.out_f32 + ((size_t)(img * p.Hl + y) * p.Wl + x) * p.out_ld + n0 + c_base;

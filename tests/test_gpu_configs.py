@@ -253,3 +253,73 @@ def test_global_stats_kernel_vs_reference_nnenc():
         moved = np.abs(got[:313].astype(np.float64) - g[name + "_hist"]).sum() * cells / 2
         print("global_stats %s: %.1f of %d cells differ from NNEncode (%d within 1e-3 of a boundary)" % (name, moved, cells, near))
         assert moved <= near + 0.01
+
+
+def _caffe_scaled(sd):
+    """A synthetic 'Caffe-scaled' weight set: conv1_1 expects raw L-50 / ab / mask*110."""
+    out = dict(sd)
+    s = torch.tensor([100.0, 110.0, 110.0, 110.0]).reshape(1, 4, 1, 1)
+    out["model1.0.weight"] = (sd["model1.0.weight"].double() / s.double()).float()
+    return out
+
+
+def test_caffe_named_wrappers(synth_sd):
+    """Rows a14 / wrapper surface: ColorizeImageB200Caffe / ...CaffeDist / ...CaffeGlobDist keep the reference's Caffe
+    class semantics (data/colorize_image.py:375-561): mask x 110, tanh x 100, 313-bin dist_ab, get_ab_reccs on
+    pts_in_hull.  Spec-only oracle (oracle/caffe_spec.py), parity unpinned."""
+    from interactive_deep_colorization_b200 import colorize_image as CI
+    g = util.golden("lhn_256.npz")
+    img = np.ascontiguousarray(g["img_rgb"][::4, ::4])                 # 64 x 64
+    ab, m = np.zeros((2, 64, 64)), np.zeros((1, 64, 64))
+    CI.put_point(ab, m, [30, 40], 3, [23, -69])
+    cc = CI.ColorizeImageB200Caffe(Xd=64)
+    assert cc.mask_mult == 110. and cc.pts_in_hull.shape == (313, 2)
+    assert cc.net_forward(ab, m) == -1                                 # "I need to have an image!"
+    cc.prep_net(0, state_dict=_caffe_scaled(synth_sd))
+    cc.set_image(img)
+    rgb = cc.net_forward(ab, m)
+    assert np.array_equal(cc.input_mask_mult, m * 110.)                # the reference attribute keeps the x110
+    L = cc.img_l_mc.astype(np.float32)[None]
+    ref = util.oracle_forward(synth_sd, L, ab[None].astype(np.float32), m[None].astype(np.float32), 0.0)[0] * (100.0 / 110.0)
+    assert util.maxabs(cc.output_ab_raw, ref) <= TOL_AB
+    assert np.array_equal(rgb, color_ref.lab2rgb_transpose(cc.img_l, cc.output_ab_raw.astype(np.float64)))
+    assert np.max(np.abs(cc.output_ab - color_ref.rgb2lab_transpose(rgb)[1:])) < 1e-9
+    # global-hints variant: zero vector == plain call; a histogram changes the result
+    sdg, gsd = _glob_sd(synth_sd)
+    cg = CI.ColorizeImageB200CaffeGlobDist(Xd=64)
+    cg.prep_net(0, state_dict=_caffe_scaled(sdg))
+    cg.set_image(img)
+    cg.net_forward(ab, m)
+    gv0 = caffe_spec.global_hints_vector(gsd, np.zeros((1, 316), np.float32))
+    ref0 = util.oracle_forward(synth_sd, L, ab[None].astype(np.float32), m[None].astype(np.float32), 0.0, glob_add=gv0)[0] * (100.0 / 110.0)
+    assert util.maxabs(cg.output_ab_raw, ref0) <= TOL_AB
+    hist = cg.get_global_histogram(np.random.RandomState(4).randint(0, 256, (120, 160, 3)).astype(np.uint8))
+    raw0 = cg.output_ab_raw.copy()
+    cg.net_forward(ab, m, hist)
+    assert util.maxabs(cg.output_ab_raw, raw0) > 0.05
+    # 313-bin distribution model
+    pts = np.load(util.os.path.join(util.GOLDEN, "pts_in_hull.npy"))
+    csd = caffe_spec.synthetic_caffe313_state_dict(pts_in_hull=pts)
+    sd313 = _caffe_scaled(synth_sd)
+    sd313.update({k: torch.from_numpy(v) for k, v in csd.items() if k != "caffe.pts_in_hull"})
+    cd = CI.ColorizeImageB200CaffeDist(Xd=64)
+    assert np.array_equal(cd.pts_grid[cd.in_hull], cd.pts_in_hull) and cd.in_hull.sum() == 313
+    cd.prep_net(0, state_dict=sd313, S=.2)
+    cd.set_image(img)
+    out = cd.net_forward(ab, m)
+    assert out.shape == (64, 64, 3) and out.dtype == np.uint8
+    _, inter = util.oracle_forward(synth_sd, L, ab[None].astype(np.float32), m[None].astype(np.float32), 0.0, intermediates=True)
+    with torch.no_grad():
+        pred64, distS64 = caffe_spec.caffe313_head(csd, inter, dtype=torch.float64)
+    assert util.maxabs(cd.output_ab_raw, pred64[0]) <= 2e-3            # spec-only head, see test_caffe313_head
+    assert np.array_equal(out, color_ref.lab2rgb_transpose(cd.img_l, cd.output_ab_raw.astype(np.float64)))
+    for (y, x) in ((0, 0), (17, 33), (63, 63)):
+        assert util.maxabs(np.asarray(cd.dist_ab[:, y, x]), distS64[0, :, y, x]) < 1e-5
+    full = cd.dist_ab_full
+    assert full.shape == (529, 64, 64) and abs(full[:, 5, 6].sum() - 1.0) < 1e-4 and full[~cd.in_hull].max() == 0.0
+    assert cd.dist_ab_grid.shape == (23, 23, 64, 64)
+    rec, conf = cd.get_ab_reccs(17, 33, K=6, return_conf=True)
+    assert rec.shape == (6, 2) and abs(conf.sum() - 1.0) < 1e-4 and np.all(np.diff(conf) <= 1e-9)
+    np.random.seed(1)
+    rec_s = cd.get_ab_reccs(17, 33, K=6, method='sampled')
+    assert rec_s.shape == (6, 2) and np.abs(rec_s).max() <= 110
