@@ -193,6 +193,16 @@ int idc_global_stats(int device, int h, int w, const uint8_t* rgb, const float* 
 int idc_zoom_lab2rgb_u8(int device, int h_in, int w_in, const double* ab, int h, int w, const double* L_full,
                         uint8_t* rgb, void* stream);
 
+/* f1, image-load side (data/colorize_image.py:52-66): cv2.resize(im, (w_dst, h_dst)) of a uint8 [h,w,3] image with
+ * OpenCV's default INTER_LINEAR -- the 8-bit path of OpenCV is fixed-point arithmetic and is restated integer for
+ * integer (bit-identical to cv2, incl. the exact-2x shortcut to area averaging).  DEVICE ptrs. */
+int idc_resize_u8_linear(int device, int h_src, int w_src, const uint8_t* src, int h_dst, int w_dst, uint8_t* dst,
+                         void* stream);
+/* f1, GUI display step (ui/gui_draw.py:280-283): cv2.resize(ab [2,h_in,w_in] float64, (w,h), INTER_CUBIC), concatenated
+ * with the window-size L [h,w] float64, skimage lab2rgb, clip, x255, truncating cast -> uint8 [h,w,3].  DEVICE ptrs. */
+int idc_cubic_lab2rgb_u8(int device, int h_in, int w_in, const double* ab, int h, int w, const double* L, uint8_t* rgb,
+                         void* stream);
+
 /* ---- introspection / test hooks (used by tests/, never by the product path) ---- */
 /* Copy a named activation ("conv1_2", "a8_1", ... see DESIGN.md) of the LAST forward to
  * out [n,C,H,W] FP32 device memory; *c,*h,*w receive its shape. */

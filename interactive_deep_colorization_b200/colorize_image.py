@@ -229,6 +229,36 @@ class ColorizeImageB200(ColorizeImageBase):
     def get_img_gray(self):
         return lab2rgb_transpose(self.img_l, np.zeros((2, self.Xd, self.Xd)))
 
+    # ----- row f1, image-load side: reference load_image :52-66 on the GPU when a net is set -----
+    def _ingest(self, rgb_full, rgb_net):
+        """Full-resolution rgb2lab (the reference spends seconds of float64 numpy on an 18 MP photo, :161-170) stays in
+        HBM as a DeviceLab; only the Xd x Xd planes come back.  `rgb_net` None = resize here with the cv2-exact kernel."""
+        big = max(rgb_full.shape[:2])
+        if not (self.gpu_prepost and self.net_set) or big > self.Xfullres_max or rgb_full.dtype != np.uint8:
+            if rgb_net is None:
+                import cv2
+                rgb_net = cv2.resize(rgb_full, (self.Xd, self.Xd)).copy()
+            return ColorizeImageBase._ingest(self, rgb_full, rgb_net)
+        from . import prepost
+        small, lab, dlab = prepost.load_image_gpu(rgb_full, self.Xd, self._device())
+        self.img_rgb_fullres = rgb_full
+        self.img_lab_fullres, self.img_l_fullres, self.img_ab_fullres = dlab, dlab.view(slice(0, 1)), dlab.view(slice(1, 3))
+        if rgb_net is None:
+            self.img_rgb = small
+            self.img_lab = lab
+        else:                                             # set_image: the caller pre-resized (reference :68-77)
+            self.img_rgb = rgb_net
+            self.img_lab = prepost.rgb2lab_gpu(rgb_net, self._device()) if rgb_net.dtype == np.uint8 else self._lab_planes(rgb_net)[0]
+        self.img_l, self.img_ab = self.img_lab[[0]], self.img_lab[1:]
+        self._set_img_lab_mc_()
+
+    def load_image(self, input_path):
+        import cv2
+        bgr = cv2.imread(input_path, 1)
+        if bgr is None:
+            raise IOError("cannot read image %r" % (input_path,))
+        self._ingest(np.ascontiguousarray(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB)), None)
+
     # ----- row f1: the numpy/scipy steps either side of the network, on the GPU when a net is set -----
     def _device(self):
         """CUDA device ordinal of the engine behind this wrapper (the Torch-named classes hold a module in

@@ -48,6 +48,10 @@ def test_no_cpu_fallback():
     from oracle import synth
     cm = ColorizeImageB200(Xd=64)
     cm.prep_net(state_dict=synth.torch_state_dict())
+    with pytest.raises(_lib.IdcError):                  # image prep runs on the GPU once a net is set (row f1)
+        cm.set_image(np.zeros((64, 64, 3), np.uint8))
+    cm = ColorizeImageB200(Xd=64, gpu_prepost=False)    # explicit host pre/post: the network itself still has no fallback
+    cm.prep_net(state_dict=synth.torch_state_dict())
     cm.set_image(np.zeros((64, 64, 3), np.uint8))
     with pytest.raises(_lib.IdcError):
         cm.net_forward(np.zeros((2, 64, 64)), np.zeros((1, 64, 64)))

@@ -323,3 +323,63 @@ def test_caffe_named_wrappers(synth_sd):
     np.random.seed(1)
     rec_s = cd.get_ab_reccs(17, 33, K=6, method='sampled')
     assert rec_s.shape == (6, 2) and np.abs(rec_s).max() <= 110
+
+
+@pytest.mark.parametrize("sh,sw,dh,dw", [(507, 600, 256, 256), (864, 1296, 256, 256), (512, 512, 256, 256),
+                                         (100, 80, 256, 256), (64, 96, 128, 192), (257, 511, 128, 128), (300, 300, 64, 64)])
+def test_resize_u8_linear_is_bit_identical_to_cv2(sh, sw, dh, dw):
+    """Row f1: `cv2.resize(im, (Xd, Xd))` of load_image (data/colorize_image.py:52-66) restated for the GPU.  OpenCV's
+    8-bit INTER_LINEAR is fixed-point; the kernel must reproduce it bit for bit (down- and up-scaling, the exact-2x
+    area shortcut, border rows / columns)."""
+    import cv2
+    from interactive_deep_colorization_b200 import prepost
+    src = np.random.RandomState(sh * 7 + sw).randint(0, 256, (sh, sw, 3)).astype(np.uint8)
+    assert np.array_equal(prepost.resize_u8_linear_gpu(src, dh, dw), cv2.resize(src, (dw, dh)))
+
+
+def test_load_image_on_gpu_matches_host_path(synth_sd, tmp_path):
+    """Row f1: ColorizeImageB200.load_image with a net set runs rgb2lab (full resolution + net size) and the resize on
+    the GPU; every attribute the reference sets must equal the host (numpy / cv2) path of the same class."""
+    import cv2
+    from scipy.ndimage import zoom
+    from interactive_deep_colorization_b200 import colorize_image as CI
+    from interactive_deep_colorization_b200.prepost import DeviceLab
+    rgb = np.random.RandomState(11).randint(0, 256, (507, 600, 3)).astype(np.uint8)
+    path = str(tmp_path / "im.png")
+    cv2.imwrite(path, np.ascontiguousarray(rgb[:, :, ::-1]))
+    gpu = CI.ColorizeImageB200(Xd=256)
+    gpu.prep_net(state_dict=synth_sd)
+    gpu.load_image(path)
+    host = CI.ColorizeImageB200(Xd=256, gpu_prepost=False)
+    host.load_image(path)                                             # no net set, gpu_prepost off: cv2 + numpy
+    assert isinstance(gpu.img_lab_fullres, DeviceLab) and gpu.img_l_fullres.shape == (1, 507, 600)
+    assert np.array_equal(gpu.img_rgb, host.img_rgb) and np.array_equal(gpu.img_rgb_fullres, host.img_rgb_fullres)
+    for name in ("img_lab", "img_l", "img_ab", "img_l_mc", "img_lab_mc", "img_lab_fullres", "img_l_fullres", "img_ab_fullres"):
+        a, b = np.asarray(getattr(gpu, name)), np.asarray(getattr(host, name))
+        assert a.shape == b.shape and np.max(np.abs(a - b)) < 1e-10, name
+    ab, m = np.zeros((2, 256, 256)), np.zeros((1, 256, 256))
+    CI.put_point(ab, m, [135, 160], 3, [23, -69])
+    gpu.net_forward(ab, m)
+    full = gpu.get_img_fullres()                                      # L stays on the device for the full-res render
+    ref = color_ref.lab2rgb_transpose(np.asarray(host.img_l_fullres),
+                                      zoom(gpu.output_ab, (1, 507 / 256., 600 / 256.), order=1))
+    d = np.abs(full.astype(int) - ref.astype(int))
+    assert full.shape == (507, 600, 3) and d.max() <= 1 and (d > 0).mean() < 1e-3
+    assert gpu.get_img_gray_fullres().shape == (507, 600, 3)
+
+
+def test_display_step_cubic_resize_lab2rgb():
+    """Row f1: the GUI's display step (ui/gui_draw.py:280-283) -- cv2 INTER_CUBIC resize of the float64 ab planes to the
+    window size + lab2rgb -- as one kernel, against cv2 + the colour oracle."""
+    import cv2
+    from interactive_deep_colorization_b200 import prepost
+    rs = np.random.RandomState(8)
+    ab = rs.uniform(-60, 60, (2, 256, 256))
+    for (H, W) in ((512, 512), (384, 600), (200, 256)):
+        l_win = rs.uniform(5, 95, (H, W))
+        got = prepost.display_rgb_gpu(ab, l_win)
+        ab_win = cv2.resize(ab.transpose((1, 2, 0)), (W, H), interpolation=cv2.INTER_CUBIC)
+        pred_lab = np.concatenate((l_win[..., np.newaxis], ab_win), axis=2)
+        ref = (np.clip(color_ref.lab2rgb(pred_lab), 0, 1) * 255).astype('uint8')
+        d = np.abs(got.astype(int) - ref.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3, (H, W, d.max(), (d > 0).mean())

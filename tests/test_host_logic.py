@@ -82,3 +82,30 @@ def test_headless_cli_hint_parsing():
     assert abs(white[0]) < 0.01 and abs(white[1]) < 0.01
     red = cli.hint_ab({"rgb": [255, 0, 0]})
     assert abs(red[0] - 80.09) < 0.05 and abs(red[1] - 67.20) < 0.05      # sRGB red in CIELAB (D65)
+
+
+def test_launcher_argument_surface_and_click_hook():
+    """Row f4: the launcher keeps ideepcolor.py's argument names (:13-46) and re-enables the per-click predict_color()
+    the reference commented out (ui/gui_draw.py:134,142) by wrapping update_ui -- checked on a stand-in class."""
+    from interactive_deep_colorization_b200 import launcher
+    a = launcher.parse_args(["--image_file", "x.jpg", "--dist_model", "w.pth", "--load_size", "128", "--win_size", "514"])
+    assert a.backend == "b200" and a.color_model == "w.pth" and a.load_size == 128 and a.gpu == 0 and not a.pytorch_maskcent
+
+    class FakeDraw(object):
+        def __init__(self):
+            self.calls, self.flag = 0, False
+
+        def update_ui(self, move_point=True):
+            return self.flag                      # is_predict: True on a new / erased point
+
+        def predict_color(self):
+            self.calls += 1
+    launcher.enable_per_click_suggestions(FakeDraw)
+    launcher.enable_per_click_suggestions(FakeDraw)          # idempotent
+    d = FakeDraw()
+    assert d.update_ui(move_point=False) is False and d.calls == 0
+    d.flag = True
+    assert d.update_ui() is True and d.calls == 1
+    import pytest
+    with pytest.raises(SystemExit):
+        launcher.build_models(launcher.parse_args(["--backend", "nope"]))
