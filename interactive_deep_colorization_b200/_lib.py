@@ -9,6 +9,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libidc_b200.so")
+if os.environ.get("IDC_B200_LIB"):            # tools only: an instrumented build (make COUNTERS=1 OUT=...)
+    LIB_PATH = os.environ["IDC_B200_LIB"]
 
 IDC_OK = 0
 FLAG_DIST = 1 << 0

@@ -1135,17 +1135,18 @@ double idc_op_flops(idc_ctx* c, int i) {
   return (c && i >= 0 && i < (int)c->ops.size()) ? c->ops[i].flops_per_image : 0.0;
 }
 
-// experiments (tools/): per-CTA cycle counters of the LAST tcgen05 launch; out[148*8] long long
+// experiments (tools/): per-CTA cycle counters of the LAST tcgen05 launch; out[148*16] long long (read + clear)
 extern "C" int idc_debug_counters(idc_ctx* c, int enable, long long* out_host) {
   if (!c) return IDC_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->dev));
   if (enable && !c->dbgbuf) {
-    CUDA_TRY(c, cudaMalloc(&c->dbgbuf, 256 * 8 * sizeof(long long)));
-    CUDA_TRY(c, cudaMemset(c->dbgbuf, 0, 256 * 8 * sizeof(long long)));
+    CUDA_TRY(c, cudaMalloc(&c->dbgbuf, 256 * 16 * sizeof(long long)));
+    CUDA_TRY(c, cudaMemset(c->dbgbuf, 0, 256 * 16 * sizeof(long long)));
   }
   if (out_host && c->dbgbuf) {
     CUDA_TRY(c, cudaDeviceSynchronize());
-    CUDA_TRY(c, cudaMemcpy(out_host, c->dbgbuf, 148 * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(c, cudaMemcpy(out_host, c->dbgbuf, 148 * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(c, cudaMemset(c->dbgbuf, 0, 256 * 16 * sizeof(long long)));
   }
   if (!enable && c->dbgbuf) { cudaFree(c->dbgbuf); c->dbgbuf = nullptr; }
   return IDC_OK;

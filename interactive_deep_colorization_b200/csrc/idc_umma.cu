@@ -353,6 +353,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
   float* s_red = reinterpret_cast<float*>(s_bar + 32);   // [128][2] fused-head partial sums, after the 256-byte barrier block
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_kernel0 = (IDC_CTA_COUNTERS && p.dbgbuf) ? clock64() : 0;
 
   // ---- one-time setup ----
   if (p.wout) {
@@ -405,7 +406,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
 
   const int tiles_per_img = p.tiles_y * p.tiles_x;
   const int G = p.chunk_kb;
-  long long t_wait_tfull_g = 0, t_drain_g = 0, t_epi_g = 0;
+  long long t_wait_tfull_g = 0, t_drain_g = 0, t_epi_g = 0, t_splitk_g = 0, t_spin_g = 0;
   const int S = p.split_k;
 
   if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
@@ -553,7 +554,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       uint32_t phase = 0;
       uint32_t cc = 0;                                   // chunk counter (persists across tiles)
       uint32_t hcount = 0;                               // HALO: halo tiles consumed
-      long long t_wait_tempty = 0, t_wait_full = 0;
+      long long t_wait_tempty = 0, t_wait_full = 0, t_first_full = 0;
       const long long t_start = clock64();
       for (int w = blockIdx.x / CG; w < p.total_tiles * S; w += gridDim.x / CG) {
         const int ks = w % S;
@@ -578,7 +579,10 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
               hslot = (hcount - 1) & 1;
             }
             mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 3);
-            if (IDC_CTA_COUNTERS && p.dbgbuf) t_wait_full += clock64() - tB;
+            if (IDC_CTA_COUNTERS && p.dbgbuf) {
+              t_wait_full += clock64() - tB;
+              if (t_first_full == 0) t_first_full = clock64() - t_kernel0;
+            }
             tc_fence_after();
             if (elect_one()) {
             const uint32_t sa = smem_u32(smem + stage * SP::kStageBytes);
@@ -638,9 +642,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         }
       }
       if (IDC_CTA_COUNTERS && p.dbgbuf && lane == 0) {
-        p.dbgbuf[blockIdx.x * 8 + 0] = clock64() - t_start;
-        p.dbgbuf[blockIdx.x * 8 + 1] = t_wait_tempty;
-        p.dbgbuf[blockIdx.x * 8 + 2] = t_wait_full;
+        p.dbgbuf[blockIdx.x * 16 + 0] = clock64() - t_start;
+        p.dbgbuf[blockIdx.x * 16 + 1] = t_wait_tempty;
+        p.dbgbuf[blockIdx.x * 16 + 2] = t_wait_full;
+        p.dbgbuf[blockIdx.x * 16 + 6] = t_first_full;          // kernel entry -> first operand stage landed
+        p.dbgbuf[blockIdx.x * 16 + 10] = t_start - t_kernel0;  // kernel entry -> MMA role entered (prologue)
       }
     }
   } else if (warp >= 4) {
@@ -655,7 +661,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
     const int t_base = (MT == 2) ? half * BN : half * CH;   // its first TMEM column inside a chunk buffer
     uint32_t cc = 0;
     int staged_key = -1;
-    long long t_epi = 0, t_wait_tfull = 0, t_drain = 0;
+    long long t_epi = 0, t_wait_tfull = 0, t_drain = 0, t_splitk = 0, t_spin = 0;
     for (int w = blockIdx.x / CG; w < p.total_tiles * S; w += gridDim.x / CG) {
       const int tile = w / S, ks = w - tile * S;
       const int kbeg = (ks * p.nkb) / S, kend = ((ks + 1) * p.nkb) / S;
@@ -764,6 +770,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
             if (seen < S && clock64() - t0 > 6000000000LL) mbar_timeout(p.err, 5);
           } while (seen < S);
+          if (IDC_CTA_COUNTERS && p.dbgbuf) t_spin += clock64() - t0;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
@@ -782,6 +789,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           }
         }
       }
+      if (IDC_CTA_COUNTERS && p.dbgbuf && S > 1) t_splitk += clock64() - tE;
       // ---- epilogue on the register accumulators, 32 output channels at a time.  The output kind is uniform for
       //      the launch, so the branch sits outside the slab loops; the per-channel vectors are read with
       //      ld.shared (warp-uniform 16-byte reads), never through generic addressing. ----
@@ -928,14 +936,17 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         }
       }
     }
-    t_wait_tfull_g = t_wait_tfull; t_drain_g = t_drain; t_epi_g = t_epi;
+    t_wait_tfull_g = t_wait_tfull; t_drain_g = t_drain; t_epi_g = t_epi; t_splitk_g = t_splitk; t_spin_g = t_spin;
   }
 
   // ---- teardown ----
   if (IDC_CTA_COUNTERS && p.dbgbuf && warp == 4 && lane == 0) {
-    p.dbgbuf[blockIdx.x * 8 + 3] = t_wait_tfull_g;
-    p.dbgbuf[blockIdx.x * 8 + 4] = t_drain_g;
-    p.dbgbuf[blockIdx.x * 8 + 5] = t_epi_g;
+    p.dbgbuf[blockIdx.x * 16 + 3] = t_wait_tfull_g;
+    p.dbgbuf[blockIdx.x * 16 + 4] = t_drain_g;
+    p.dbgbuf[blockIdx.x * 16 + 5] = t_epi_g;
+    p.dbgbuf[blockIdx.x * 16 + 7] = clock64() - t_kernel0;     // CTA lifetime up to the teardown
+    p.dbgbuf[blockIdx.x * 16 + 8] = t_splitk_g;                // split-K: park + wait + reduce
+    p.dbgbuf[blockIdx.x * 16 + 9] = t_spin_g;                  // split-K: of which spinning for the other slices
   }
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();   // pairs: the peer may still arrive on / read from this CTA
