@@ -138,6 +138,14 @@ int idc_forward_host_q(idc_ctx* ctx, int n, int h, int w, const float* L_mc, con
                        const float* mask, float maskcent, const float* glob, float* out_ab,
                        float* out_dist, uint8_t* out_rgb, double* out_abq);
 
+/* Page-locked host memory for the zero-copy click path: when every buffer handed to idc_forward_host(_q) with
+ * n <= 4 comes from idc_host_alloc (or is otherwise pinned), the copy nodes of the click graph read / write the caller's
+ * memory directly (no staging copy by the CPU); buffers laid out back to back -- [L | ab | mask (| glob)] and
+ * [out_ab | out_rgb | out_abq] -- travel as one copy each way.  The graph is re-captured when the pointers change, so
+ * keep the buffers for the lifetime of the session (LhnContext.click_buffers does). */
+void* idc_host_alloc(size_t bytes);
+int idc_host_free(void* p);
+
 /* Interactive path: keep the 529-bin distribution of the last idc_forward_host on the device instead
  * of copying all of it back (8.7 MB at 256^2) -- the reference only ever reads one pixel of it per click
  * (`self.dist_ab[:, h, w]`, data/colorize_image.py:329).  With resident mode on, idc_forward_host runs the

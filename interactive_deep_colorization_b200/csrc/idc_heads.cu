@@ -33,7 +33,7 @@ __device__ __forceinline__ float div_corrected(float a, float d, float rd) {
 }
 
 template <bool SPLIT>
-__global__ void __launch_bounds__(128) conv1_1_kernel(const __grid_constant__ Conv11Weights W,
+__global__ void __launch_bounds__(128, 4) conv1_1_kernel(const __grid_constant__ Conv11Weights W,
                                                       const float* __restrict__ L, const float* __restrict__ ab,
                                                       const float* __restrict__ mask, float maskcent, int N, int H,
                                                       int Wd, float* __restrict__ outf, __half* __restrict__ ohi,

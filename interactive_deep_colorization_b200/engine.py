@@ -49,6 +49,7 @@ class LhnContext(object):
                                     "required; there is no CPU fallback" % (device, max_n, H, W))
         self.h = h
         self.ready = False
+        self._pinned = []
         for k, v in (options or {}).items():
             self.set_option(k, v)
 
@@ -112,7 +113,7 @@ class LhnContext(object):
         return {"ab": out_ab, "dist": out_dist if want_dist else None, "rgb": out_rgb if want_rgb else None}
 
     def forward_host(self, L_mc, ab, mask, maskcent=0.0, glob=None, want_dist=False, want_rgb=False,
-                     out_ab=None, out_dist=None, out_rgb=None, want_abq=False):
+                     out_ab=None, out_dist=None, out_rgb=None, want_abq=False, out_abq=None):
         """numpy float32 C-contiguous host arrays (pinned or pageable) -> dict of numpy arrays.
         Synchronous; includes H2D + D2H.  want_abq: also the reference's quantised output_ab
         (rgb2lab(rgb)[1:], float64; implies want_rgb)."""
@@ -126,7 +127,8 @@ class LhnContext(object):
             out_dist = np.empty((n, 529, self.H // 4, self.W // 4), np.float32)
         if want_rgb and out_rgb is None:
             out_rgb = np.empty((n, self.H, self.W, 3), np.uint8)
-        out_abq = np.empty((n, 2, self.H, self.W), np.float64) if want_abq else None
+        if want_abq and out_abq is None:
+            out_abq = np.empty((n, 2, self.H, self.W), np.float64)
         rc = self.lib.idc_forward_host_q(self.h, n, self.H, self.W, _np_ptr(L_mc), _np_ptr(ab), _np_ptr(mask),
                                          float(maskcent), _np_ptr(glob) if glob is not None else None,
                                          _np_ptr(out_ab), _np_ptr(out_dist) if want_dist else None,
@@ -135,6 +137,32 @@ class LhnContext(object):
         _lib.check(self.h, rc)
         return {"ab": out_ab, "dist": out_dist if want_dist else None, "rgb": out_rgb if want_rgb else None,
                 "abq": out_abq}
+
+    # ---- zero-copy click path ---------------------------------------------------------------
+    def click_buffers(self, n=1, glob=False):
+        """Page-locked I/O arrays for the interactive call (n <= 4), laid out back to back so that a click is one H2D and
+        one D2H with NO copy by the CPU: pass them to forward_host (L_mc / ab / mask (/ glob) as inputs, out_ab / out_rgb /
+        out_abq as outputs).  -> dict of numpy views; they stay valid until close()."""
+        HW = self.H * self.W
+        n_in = n * 4 * HW + (n * 316 if glob else 0)
+        b_ab, b_rgb, b_q = n * 2 * HW * 4, n * 3 * HW, n * 2 * HW * 8
+        sizes = (n_in * 4, b_ab + b_rgb + b_q)
+        blocks = []
+        for nbytes in sizes:
+            p = self.lib.idc_host_alloc(nbytes)
+            if not p:
+                raise _lib.IdcError(-2, "idc_host_alloc(%d) failed" % nbytes)
+            self._pinned.append(p)
+            blocks.append(np.frombuffer((ctypes.c_char * nbytes).from_address(p), dtype=np.uint8))
+        fin = blocks[0].view(np.float32)
+        out = {"L_mc": fin[:n * HW].reshape(n, 1, self.H, self.W),
+               "ab": fin[n * HW:3 * n * HW].reshape(n, 2, self.H, self.W),
+               "mask": fin[3 * n * HW:4 * n * HW].reshape(n, 1, self.H, self.W),
+               "glob": fin[4 * n * HW:].reshape(n, 316) if glob else None,
+               "out_ab": blocks[1][:b_ab].view(np.float32).reshape(n, 2, self.H, self.W),
+               "out_rgb": blocks[1][b_ab:b_ab + b_rgb].reshape(n, self.H, self.W, 3),
+               "out_abq": blocks[1][b_ab + b_rgb:].view(np.float64).reshape(n, 2, self.H, self.W)}
+        return out
 
     def set_dist_resident(self, on=True):
         """Interactive mode: the dist head runs on every forward_host but stays on the device."""
@@ -225,6 +253,9 @@ class LhnContext(object):
         if getattr(self, "h", None):
             self.lib.idc_destroy(self.h)
             self.h = None
+            for p in getattr(self, "_pinned", []):
+                self.lib.idc_host_free(p)
+            self._pinned = []
 
     def __del__(self):
         try:
