@@ -40,24 +40,24 @@ if ROOT not in sys.path:
 METRIC = "net_forward images/sec @256x256"   # --size 512 reports the same metric name with the size in config
 X = 256
 PER_GPU_BATCH = 64
-NCU_TRAFFIC_CSV = os.path.join(ROOT, "profiles", "r02_ncu_full_umma_conv_batch64.csv")
+NCU_TRAFFIC_CSV = os.path.join(ROOT, "profiles", "r02_ncu_full_batch64_forward.csv")
 
 
 def _ncu_traffic(batch, size):
-    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed `ncu --set full`
-    capture of this same workload at HEAD (profiles/r02_ncu_full_umma_conv_batch64.csv)."""
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel (mean over the 25 umma_conv launches of
+    the regression trunk), from the committed `ncu --set full` capture of this same workload at HEAD
+    (profiles/r02_ncu_full_batch64_forward.csv, written by tools/ncu_summary.py)."""
     if batch != 64 or size != 256 or not os.path.isfile(NCU_TRAFFIC_CSV):
         return None
+    import csv
+    rows = list(csv.reader(l for l in open(NCU_TRAFFIC_CSV) if not l.startswith("#")))
+    h = rows[0]
     tot, n = 0.0, 0
-    for line in open(NCU_TRAFFIC_CSV):
-        if line.startswith("#") or line.startswith("op,"):
-            continue
-        f = line.strip().split('",')
-        if len(f) < 2:
-            continue
-        v = f[1].split(",")
-        tot += (float(v[2]) + float(v[3])) * 1e9          # dram_read[Gbyte], dram_write[Gbyte]
-        n += 1
+    for r in rows[1:]:
+        d = dict(zip(h, r))
+        if d["kernel"].startswith("umma_conv_kernel") and d["op"] != "class":
+            tot += (float(d["dram_read_MB"]) + float(d["dram_write_MB"])) * 1e6
+            n += 1
     return tot / n if n else None
 
 
@@ -325,11 +325,29 @@ def run_latency(local, L):
         t = time.perf_counter()       # not part of config 5: the K=9 colour suggestions the GUI shows (row f2)
         lctx.ab_reccs(0, int(loc[0]) // 4, int(loc[1]) // 4, K=9)
         reccs_times.append((time.perf_counter() - t) * 1e3)
+    pageable = times[5:]
+    # the same 20 clicks with the context's page-locked click buffers (LhnContext.click_buffers / idc_host_alloc): the
+    # copy nodes of the graph read / write the caller's memory, no CPU staging copy
+    buf = lctx.click_buffers(1)
+    buf["L_mc"][...] = l1
+    buf["ab"][...] = 0
+    buf["mask"][...] = 0
+    times = []
+    for i in range(25):
+        loc = rs.randint(8, X - 8, 2)
+        CI.put_point(buf["ab"][0], buf["mask"][0], loc, 3, rs.uniform(-80, 80, 2))
+        t = time.perf_counter()
+        lctx.forward_host(buf["L_mc"], buf["ab"], buf["mask"], 0.5, want_rgb=True, out_ab=buf["out_ab"], out_rgb=buf["out_rgb"])
+        lctx.fetch_dist(0, int(loc[0]) // 4, int(loc[1]) // 4)
+        times.append((time.perf_counter() - t) * 1e3)
     times = times[5:]
     lat = {"p50_ms": float(np.percentile(times, 50)), "p99_ms": float(np.percentile(times, 99)),
+           "pageable_p50_ms": float(np.percentile(pageable, 50)), "pageable_p99_ms": float(np.percentile(pageable, 99)),
            "reccs_k9_p50_ms": float(np.percentile(reccs_times[5:], 50)), "calls": len(times),
            "what": "BASELINE config 5: put_point -> C-ABI idc_forward_host (batch 1, dist head + Lab->RGB on, one CUDA graph: "
-                   "H2D of L/hints, PDL-chained kernels, D2H of ab + rgb) + idc_fetch_dist of the clicked pixel"}
+                   "H2D of L/hints, PDL-chained kernels with the dist head on a side branch, D2H of ab + rgb) + idc_fetch_dist of "
+                   "the clicked pixel; p50/p99 with the page-locked click buffers of the API (zero CPU copies), pageable_* with "
+                   "ordinary numpy arrays (staged by the CPU)"}
     lctx.close()
     # wrapper level, as ui/gui_draw.py:258-286 calls it: colour model net_forward (RGB + quantised output_ab),
     # dist model net_forward + get_ab_reccs (predict_color / suggest_color)
@@ -399,8 +417,9 @@ def run_ours(args):
     cL, cab, cm_ = synth.synthetic_batch(1, X, seed=424242, max_hints=10)
     cout = ctx.forward_device(torch.from_numpy(cL).to(dev), torch.from_numpy(cab).to(dev), torch.from_numpy(cm_).to(dev), 0.5)["ab"]
     torch.cuda.synchronize(dev)
-    csum = torch.stack([cout.double().sum(), cout.double().abs().sum(),
-                        (cout.view(torch.int32).to(torch.int64) & 0xFFFF).sum().double()])
+    hc = cout.cpu().numpy()                                 # checksums on the host: no library kernel on the GPU
+    csum = torch.tensor([float(hc.astype(np.float64).sum()), float(np.abs(hc.astype(np.float64)).sum()),
+                         float((hc.view(np.int32).astype(np.int64) & 0xFFFF).sum())], dtype=torch.float64, device=dev)
     if world > 1:
         allsums = [torch.zeros_like(csum) for _ in range(world)]
         dist.all_gather(allsums, csum)

@@ -82,6 +82,7 @@ int idc_create(int device, int max_n, int h, int w, unsigned flags, idc_ctx** ou
  *   "direct_stores" 0 / 1       per-lane 16-byte stores instead of the warp-transposed ones
  *   "host_pipe"     0 / 1       idc_forward_host: chunked copy/compute overlap for batches >= 8
  *   "pdl"           0 / 1       programmatic dependent launch between the kernels of one forward
+ *   "side_dist"     0 / 1       batches <= 4: run the dist head (class + softmax) on a side stream / graph branch
  *   "tanh_scale"    110 / 100   regression head scale: tanh * 110 (model.py:175) or the Caffe nets' 100
  *                               (models/reference_model/deploy_nodist.prototxt:812-822)
  * Unknown names return IDC_ERR_KEY. */

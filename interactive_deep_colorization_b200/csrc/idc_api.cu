@@ -521,7 +521,33 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
     CUDA_TRY(c, launch_conv1_1(c, n, L, ab, mask, maskcent, st));
   }
   mark();
+  // Interactive batches: the dist head (class 1x1 conv + 529-way softmax) only depends on conv8_3, and decoder levels
+  // 9-10 do not depend on it -> it runs on a side stream (a parallel branch of the click graph) on the ~20 SMs the
+  // 128-CTA launches of the main chain leave idle, instead of sitting between c8_3 and up9 on the critical path.
+  const bool side_dist = c->opt.side_dist && !c->simt && out_dist && n <= 4 && !hp && !ev;
+  bool forked = false;
   for (auto& op : c->ops) {
+    if (side_dist && op.kind == OP_CLASS && op.name == "class") {
+      if (!c->s_side) {
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_side, cudaStreamNonBlocking));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+      }
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      CUDA_TRY(c, cudaStreamIsCapturing(st, &cap));
+      const bool main_chain = c->chain;
+      CUDA_TRY(c, cudaEventRecord(c->ev_fork, st));
+      CUDA_TRY(c, cudaStreamWaitEvent(c->s_side, c->ev_fork, 0));
+      pdl_break(c);                                        // first kernel of the branch follows an event wait
+      CUDA_TRY(c, umma_run_op(c, op, n, nullptr, (float)c->opt.tanh_scale, c->s_side, 0, 16));
+      CUDA_TRY(c, launch_softmax529(c, n, out_dist, c->s_side));     // PDL-chained behind `class` on the side stream
+      CUDA_TRY(c, cudaEventRecord(c->ev_join, c->s_side));
+      // in a capture the event record is not a node: up9 keeps its programmatic edge to c8_3; on a live stream the
+      // record sits between the two kernels, so the next launch is serialised normally
+      c->chain = (cap == cudaStreamCaptureStatusActive) ? main_chain : false;
+      forked = true;
+      continue;
+    }
     if (c->simt) {
       CUDA_TRY(c, simt_run_op(c, op, n, st));
     } else if (hp && op.fuse_out_head) {
@@ -541,10 +567,14 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
   }
   const bool fused = !c->simt && !(c->flags & IDC_FLAG_KEEP_CONV10);
   if (!fused) CUDA_TRY(c, launch_out_head(c, n, out_ab, st));
-  if (out_dist) CUDA_TRY(c, launch_softmax529(c, n, out_dist, st));
+  if (out_dist && !forked) CUDA_TRY(c, launch_softmax529(c, n, out_dist, st));
   if (out_rgb) {
     CUDA_TRY(c, launch_lab2rgb(c, n, c->H, c->W, L, 50.0f, out_ab, out_rgb, st, out_abq));
     c->launch_count++;
+  }
+  if (forked) {
+    CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_join, 0));   // join: whatever follows on `st` sees the distribution
+    pdl_break(c);
   }
   mark();
   pdl_break(c);
@@ -604,11 +634,12 @@ int idc_set_option(idc_ctx* c, const char* name, int value) {
   struct { const char* n; int* v; } tab[] = {
       {"halo", &c->opt.halo}, {"pairs", &c->opt.pairs}, {"mt", &c->opt.mt}, {"chunk_kb", &c->opt.chunk_kb},
       {"split_k", &c->opt.split_k}, {"direct_stores", &c->opt.direct_stores}, {"host_pipe", &c->opt.host_pipe},
-      {"pdl", &c->opt.pdl}, {"split_pairs", &c->opt.split_pairs}, {"tanh_scale", &c->opt.tanh_scale}};
+      {"pdl", &c->opt.pdl}, {"split_pairs", &c->opt.split_pairs}, {"tanh_scale", &c->opt.tanh_scale},
+      {"side_dist", &c->opt.side_dist}};
   for (auto& t : tab)
     if (!strcmp(t.n, name)) {
       *t.v = value;
-      if (c->weights_ready && strcmp(name, "host_pipe") && strcmp(name, "tanh_scale")) {      // plan-time option changed after planning: re-plan
+      if (c->weights_ready && strcmp(name, "host_pipe") && strcmp(name, "tanh_scale") && strcmp(name, "side_dist")) {      // plan-time option changed after planning: re-plan
         CUDA_TRY(c, cudaSetDevice(c->dev));
         CUDA_TRY(c, cudaDeviceSynchronize());
         int rc = plan_engines(c);
@@ -1254,6 +1285,7 @@ int idc_destroy(idc_ctx* c) {
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_rgb) cudaFreeHost(c->h_rgb);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->s_side) { cudaStreamDestroy(c->s_side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
   if (c->s_in) {
     cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);
     for (int k = 0; k < HostPipe::kMaxChunks; ++k) { cudaEventDestroy(c->ev_in[k]); cudaEventDestroy(c->ev_out[k]); }

@@ -118,6 +118,7 @@ struct Options {
   int host_pipe = 1;      // idc_forward_host: chunked copy/compute overlap for batches >= 8
   int pdl = 1;            // programmatic dependent launch between the kernels of a forward
   int split_pairs = 1;    // cta_group::2 on the split-K (small batch) path
+  int side_dist = 1;      // batch <= 4: run the dist head (class + softmax) on a side stream next to levels 9-10
   int tanh_scale = 110;   // regression head: tanh * 110 (model.py:175); the Caffe deploy nets use 100
 };
 
@@ -174,6 +175,9 @@ struct Ctx {
   // idc_forward_host pipeline (large batches): H2D of image chunk k+1 overlaps conv1_1 of chunk k, D2H of ab
   // chunk k overlaps the last op of chunk k+1
   cudaStream_t s_in = nullptr, s_out = nullptr;
+  // dist head off the critical path: class + softmax run on a side stream next to decoder levels 9-10
+  cudaStream_t s_side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_in[8] = {}, ev_out[8] = {};
   // CUDA graph cache for the batch-1 latency path
   cudaGraphExec_t graph_exec = nullptr;
@@ -198,7 +202,8 @@ struct Ctx {
 cudaError_t simt_run_op(Ctx* c, ConvOp& op, int n, cudaStream_t st);
 int umma_plan_op(Ctx* c, ConvOp& op);              // builds tensor maps; returns IDC_* code
 void umma_free_op(ConvOp& op);
-cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float out_mult, cudaStream_t st, int img0 = 0);
+cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float out_mult, cudaStream_t st, int img0 = 0,
+                        int max_ctas = 0);   // max_ctas > 0: cap the persistent grid (side-branch launches)
 bool umma_op_uses_split_k(const ConvOp& op);
 
 cudaError_t launch_conv1_1(Ctx* c, int n, const float* L, const float* ab, const float* mask,

@@ -69,6 +69,7 @@ struct UmmaParams {
   int* err;
   long long* dbgbuf;   // experiments only: per-CTA cycle counters [grid][8]
   int n_amaps;         // entries of `amaps` (prefetched in the prologue)
+  int max_ctas;        // host side only: grid cap for side-branch launches
   int halo_groups;     // HALO kernels: 64-channel input groups (K = 9 taps x halo_groups k-blocks); kblk = {-, B k-column, dy+1, dx+1}
   int img0;            // first image of this launch (n_img = img0 + images of the launch): idc_forward_host
                        // runs the last op in image chunks so that the D2H of a chunk overlaps the next one
@@ -1031,6 +1032,7 @@ static cudaError_t launch_inst(const UmmaPlan& pl, const UmmaParams& prm, cudaSt
   }
   const long items = (long)prm.total_tiles * prm.split_k;
   int grid = items * CG < pl.num_sms ? (int)items * CG : (pl.num_sms / CG) * CG;
+  if (prm.max_ctas > 0 && grid > prm.max_ctas) grid = prm.max_ctas;   // persistent loop: any grid size covers all tiles
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
@@ -1112,7 +1114,10 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
     const bool can = !c->fast && (op.bn_tile == 256 || op.bn_tile == 128 || (op.bn_tile == 64 && (pl->mt == 2 || pl->halo)));
     const long tiles_mt = tiles1 / pl->mt;
     const int mode = c->opt.pairs;   // 0 = off, 1 (default) = launches that give every SM pair >= 2 tiles, 2 = always
-    if (can && (mode >= 2 || (mode == 1 && tiles_mt >= 4L * pl->num_sms))) pl->cg = 2;
+    // >= 2 tiles per SM (= 4 per pair).  Measured at batch 1 (profiles/r02_latency_per_op.txt): up10 62 -> 55 us,
+    // c10_2 65 -> 49 us with pairs -- these launches re-fetch their weight tile per 128-pixel tile and are bound by the
+    // L2 -> SM operand traffic, which a pair halves for the weights.
+    if (can && (mode >= 2 || (mode == 1 && tiles_mt >= 2L * pl->num_sms))) pl->cg = 2;
   }
   const int nkb = op.K / kBK;
   // split-K for launches that cannot fill the machine even at the ctx's max batch (interactive path): K is cut into S
@@ -1287,10 +1292,12 @@ bool umma_op_uses_split_k(const ConvOp& op) {
   return pl && pl->split_k > 1;
 }
 
-cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float out_mult, cudaStream_t st, int img0) {
+cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float out_mult, cudaStream_t st, int img0,
+                        int max_ctas) {
   UmmaPlan* pl = static_cast<UmmaPlan*>(op.umma_plan);
   if (!pl) return cudaErrorInvalidValue;
   UmmaParams prm = pl->prm;
+  prm.max_ctas = (max_ctas > 0 && pl->split_k == 1 && pl->cg == 1) ? max_ctas : 0;
   prm.img0 = img0;
   prm.n_img = img0 + n;
   if (img0 && pl->split_k > 1) return cudaErrorInvalidValue;   // image chunks are a large-batch feature

@@ -138,7 +138,7 @@ def test_fast_fp16_forward_host_large_batch(synth_sd):
 
 
 def test_plan_options_agree(synth_sd):
-    """PDL on/off must be bit-identical (same kernels, same order of arithmetic); CTA pairs on the split-K path and
+    """PDL on/off and the side-stream dist head on/off must be bit-identical (same kernels, same order of arithmetic); CTA pairs on the split-K path and
     the halo-tile operand change the summation order only: each variant within tolerance of the oracle and within
     3e-4 of each other.  256^2, batch 1 (the interactive plan: split-K everywhere) and batch 4."""
     g = util.golden("lhn_256.npz")
@@ -147,8 +147,8 @@ def test_plan_options_agree(synth_sd):
     a1, m1 = a1[None].astype(np.float32), m1[None].astype(np.float32)
     ref = g["mc1_rand5_ab_raw"]
     outs = {}
-    for name, opts in (("default", {}), ("no_pdl", {"pdl": 0}), ("no_split_pairs", {"split_pairs": 0}),
-                       ("no_halo", {"halo": 0}), ("halo_all", {"halo": 3})):
+    for name, opts in (("default", {}), ("no_pdl", {"pdl": 0}), ("no_side_dist", {"side_dist": 0}),
+                       ("no_split_pairs", {"split_pairs": 0}), ("no_halo", {"halo": 0}), ("halo_all", {"halo": 3})):
         ctx = util.make_ctx(synth_sd, 256, 256, max_n=1, dist=True, options=opts)
         r = ctx.forward_host(L1, a1, m1, 0.5, want_dist=True, want_rgb=True)
         r2 = ctx.forward_host(L1, a1, m1, 0.5, want_dist=True, want_rgb=True)      # graph replay
@@ -158,8 +158,10 @@ def test_plan_options_agree(synth_sd):
         assert err <= TOL_AB, (name, err)
         outs[name] = r
         ctx.close()
-    assert np.array_equal(outs["default"]["ab"], outs["no_pdl"]["ab"])
-    assert np.array_equal(outs["default"]["dist"], outs["no_pdl"]["dist"])
+    for k in ("no_pdl", "no_side_dist"):                               # scheduling only: bit-identical
+        assert np.array_equal(outs["default"]["ab"], outs[k]["ab"]), k
+        assert np.array_equal(outs["default"]["dist"], outs[k]["dist"]), k
+        assert np.array_equal(outs["default"]["rgb"], outs[k]["rgb"]), k
     for k in ("no_split_pairs", "no_halo", "halo_all"):
         assert util.maxabs(outs[k]["ab"], outs["default"]["ab"]) < 3e-4, k
     # batch 4 on a max_n = 4 context (halo + pairs plans differ from the batch-1 context)

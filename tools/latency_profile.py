@@ -44,16 +44,25 @@ def run(tag, options, per_op=True):
         print("[%s] stream-launched forward (dist+rgb): %.1f us each" % (tag, e0.elapsed_time(e1) * 1e3 / 50))
         ctx.close()
     for want_dist in (True, False):
-        ctx = util.make_ctx(sd, 256, 256, max_n=1, dist=True, use_graph=True, options=options)
-        if want_dist:
-            ctx.set_dist_resident(True)
-        ts = []
-        for i in range(40):
-            t = time.perf_counter()
-            ctx.forward_host(L, ab, m, 0.5, want_rgb=True, want_abq=True)
-            ts.append((time.perf_counter() - t) * 1e3)
-        print("[%s] forward_host_q graph resident_dist=%s p50 %.3f ms  min %.3f ms" % (tag, want_dist, np.percentile(ts[5:], 50), min(ts)))
-        ctx.close()
+        for pinned in (False, True):
+            ctx = util.make_ctx(sd, 256, 256, max_n=1, dist=True, use_graph=True, options=options)
+            if want_dist:
+                ctx.set_dist_resident(True)
+            kw = {}
+            a, b, c = L, ab, m
+            if pinned:
+                buf = ctx.click_buffers(1)
+                buf["L_mc"][...] = L; buf["ab"][...] = ab; buf["mask"][...] = m
+                a, b, c = buf["L_mc"], buf["ab"], buf["mask"]
+                kw = dict(out_ab=buf["out_ab"], out_rgb=buf["out_rgb"], out_abq=buf["out_abq"])
+            ts = []
+            for i in range(40):
+                t = time.perf_counter()
+                ctx.forward_host(a, b, c, 0.5, want_rgb=True, want_abq=True, **kw)
+                ts.append((time.perf_counter() - t) * 1e3)
+            print("[%s] forward_host_q graph resident_dist=%s %s buffers p50 %.3f ms  min %.3f ms"
+                  % (tag, want_dist, "page-locked" if pinned else "pageable", np.percentile(ts[5:], 50), min(ts)))
+            ctx.close()
 
 
 if __name__ == "__main__":
