@@ -1148,6 +1148,17 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
       if (S2 > op.bn_tile / 32) S2 = op.bn_tile / 32;
       if (c->opt.split_k >= 1 && c->opt.split_k <= S2) S2 = c->opt.split_k;
       if (S2 >= 2) { pl->cg = 2; S = S2; Tw = T2 * 2; }
+      // 128-column tiles on the split path: the partial tile a CTA parks / reduces through L2 is 64 KB instead of
+      // 128 KB (the split-K section is L2-bandwidth bound), at the price of a shared-memory-bound N=128 MMA phase.
+      if (c->opt.split_bn128 && op.bn_tile == 256 && S2 >= 2) {
+        const int ntn2 = op.cout_pad / 128;
+        const long T3 = (long)op.ncls * ((m_tiles + 1) / 2) * ntn2;
+        int S3 = (int)((pl->num_sms / 2) / T3);
+        if (S3 > nkb / 4) S3 = nkb / 4;
+        if (S3 > 4) S3 = 4;                                // 128 columns = 4 pieces of 32
+        if (c->opt.split_k >= 1 && c->opt.split_k <= S3) S3 = c->opt.split_k;
+        if (S3 >= 2) { op.bn_tile = 128; S = S3; Tw = T3 * 2; }
+      }
     }
     pl->split_k = S;
     pl->ws_tiles = (int)Tw;                                // reduction slots: (pair-)tiles x CTAs per tile
