@@ -844,10 +844,13 @@ static int forward_host_small(idc_ctx* c, int n, const float* L, const float* ab
     c->graph_maskcent = maskcent;
     c->graph_launches = c->launch_count;
   }
+  if (c->dbg_graph_timing) CUDA_TRY(c, cudaEventRecord(c->dbg_ev[0], st));
   CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, st));
+  if (c->dbg_graph_timing) CUDA_TRY(c, cudaEventRecord(c->dbg_ev[1], st));
   c->launch_count = c->graph_launches;
   c->last_n = n;
   CUDA_TRY(c, cudaStreamSynchronize(st));
+  if (c->dbg_graph_timing) cudaEventElapsedTime(&c->dbg_graph_ms, c->dbg_ev[0], c->dbg_ev[1]);
   if (!direct) {
     memcpy(out_ab, hsm, b_ab);
     if (want_rgb) memcpy(out_rgb, hsm + b_ab, b_rgb);
@@ -1240,6 +1243,20 @@ extern "C" int idc_debug_counters(idc_ctx* c, int enable, long long* out_host) {
   return IDC_OK;
 }
 
+// experiments (tools/click_breakdown.py): device time of the click graph (copy nodes included), measured with two
+// events around the graph launch.  enable = 1 / 0; returns the last span in *ms when non-null.
+extern "C" int idc_debug_graph_timing(idc_ctx* c, int enable, float* ms) {
+  if (!c) return IDC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  if (enable && !c->dbg_ev[0]) {
+    CUDA_TRY(c, cudaEventCreate(&c->dbg_ev[0]));
+    CUDA_TRY(c, cudaEventCreate(&c->dbg_ev[1]));
+  }
+  c->dbg_graph_timing = enable != 0 && c->dbg_ev[0];
+  if (ms) *ms = c->dbg_graph_ms;
+  return IDC_OK;
+}
+
 int idc_num_ops(idc_ctx* c) { return c ? (int)c->ops.size() : 0; }
 const char* idc_op_name(idc_ctx* c, int i) {
   return (c && i >= 0 && i < (int)c->ops.size()) ? c->ops[i].name.c_str() : nullptr;
@@ -1284,6 +1301,7 @@ int idc_destroy(idc_ctx* c) {
   if (c->h_in) cudaFreeHost(c->h_in);
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_rgb) cudaFreeHost(c->h_rgb);
+  if (c->dbg_ev[0]) { cudaEventDestroy(c->dbg_ev[0]); cudaEventDestroy(c->dbg_ev[1]); }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->s_side) { cudaStreamDestroy(c->s_side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
   if (c->s_in) {

@@ -164,6 +164,9 @@ struct Ctx {
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;
   int* splitk_counters = nullptr; int splitk_max_tiles = 0;
   long long* dbgbuf = nullptr;   // experiments: per-CTA cycle counters of the last tcgen05 launch
+  bool dbg_graph_timing = false; // experiments: events around the click graph launch (idc_debug_graph_timing)
+  cudaEvent_t dbg_ev[2] = {nullptr, nullptr};
+  float dbg_graph_ms = 0.f;
   int* d_err = nullptr;        // watchdog flag (mapped pinned host memory: survives a device trap)
   int* h_err = nullptr;
   // staging for idc_forward_host
