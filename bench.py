@@ -326,7 +326,7 @@ def run_latency(local, L):
         lctx.ab_reccs(0, int(loc[0]) // 4, int(loc[1]) // 4, K=9)
         reccs_times.append((time.perf_counter() - t) * 1e3)
     pageable = times[5:]
-    # the same 20 clicks with the context's page-locked click buffers (LhnContext.click_buffers / idc_host_alloc): the
+    # the same clicks with the context's page-locked click buffers (LhnContext.click_buffers / idc_host_alloc): the
     # copy nodes of the graph read / write the caller's memory, no CPU staging copy
     buf = lctx.click_buffers(1)
     buf["L_mc"][...] = l1
@@ -340,44 +340,75 @@ def run_latency(local, L):
         lctx.forward_host(buf["L_mc"], buf["ab"], buf["mask"], 0.5, want_rgb=True, out_ab=buf["out_ab"], out_rgb=buf["out_rgb"])
         lctx.fetch_dist(0, int(loc[0]) // 4, int(loc[1]) // 4)
         times.append((time.perf_counter() - t) * 1e3)
+    unannounced = times[5:]
+    # the shipped click: the image is resident (idc_set_image, once per photo -- the reference's set_image / net_forward
+    # split), the click is announced (idc_set_click) so its pmf AND the K=9 suggestions ride on the dist head's side
+    # branch of the same graph; everything the GUI shows after a click is inside the timed region
+    lctx.set_image(buf["L_mc"])
+    times = []
+    for i in range(25):
+        loc = rs.randint(8, X - 8, 2)
+        CI.put_point(buf["ab"][0], buf["mask"][0], loc, 3, rs.uniform(-80, 80, 2))
+        y4, x4 = int(loc[0]) // 4, int(loc[1]) // 4
+        t = time.perf_counter()
+        lctx.set_click(0, y4, x4, 9)
+        lctx.forward_host(None, buf["ab"], buf["mask"], 0.5, want_rgb=True, out_ab=buf["out_ab"], out_rgb=buf["out_rgb"])
+        lctx.fetch_dist(0, y4, x4)
+        lctx.ab_reccs(0, y4, x4, K=9)
+        times.append((time.perf_counter() - t) * 1e3)
     times = times[5:]
     lat = {"p50_ms": float(np.percentile(times, 50)), "p99_ms": float(np.percentile(times, 99)),
+           "unannounced_p50_ms": float(np.percentile(unannounced, 50)), "unannounced_p99_ms": float(np.percentile(unannounced, 99)),
            "pageable_p50_ms": float(np.percentile(pageable, 50)), "pageable_p99_ms": float(np.percentile(pageable, 99)),
            "reccs_k9_p50_ms": float(np.percentile(reccs_times[5:], 50)), "calls": len(times),
-           "what": "BASELINE config 5: put_point -> C-ABI idc_forward_host (batch 1, dist head + Lab->RGB on, one CUDA graph: "
-                   "H2D of L/hints, PDL-chained kernels with the dist head on a side branch, D2H of ab + rgb) + idc_fetch_dist of "
-                   "the clicked pixel; p50/p99 with the page-locked click buffers of the API (zero CPU copies), pageable_* with "
-                   "ordinary numpy arrays (staged by the CPU)"}
+           "what": "BASELINE config 5: put_point -> idc_set_click (pixel + K=9) -> C-ABI idc_forward_host (batch 1, resident "
+                   "image, dist head + Lab->RGB on, one CUDA graph: H2D of the hints, PDL-chained kernels, the dist head + the "
+                   "clicked pixel's pmf + its 9 colour suggestions on a side branch, D2H of ab + rgb) -> idc_fetch_dist + "
+                   "idc_ab_reccs (host-side reads); page-locked click buffers.  unannounced_*: round-2 protocol (L re-sent, "
+                   "pmf fetched by a separate device call, no suggestions; reccs_k9 = what a separate suggestion call costs). "
+                   "pageable_*: ordinary numpy arrays (staged by the CPU)"}
     lctx.close()
     # wrapper level, as ui/gui_draw.py:258-286 calls it: colour model net_forward (RGB + quantised output_ab),
     # dist model net_forward + get_ab_reccs (predict_color / suggest_color)
     import contextlib
     import io
-    with contextlib.redirect_stdout(io.StringIO()):
-        cm = CI.ColorizeImageB200(Xd=X, maskcent=True)
-        cm.prep_net(state_dict=sd)
-        cd = CI.ColorizeImageB200Dist(Xd=X, maskcent=True)
-        cd.prep_net(state_dict=sd)
     img = np.random.RandomState(1).randint(0, 256, (X, X, 3)).astype(np.uint8)
-    cm.set_image(img); cd.set_image(img)
-    ab64, m64 = np.zeros((2, X, X)), np.zeros((1, X, X))
-    t_col, t_all = [], []
-    for i in range(25):
-        loc = rs.randint(8, X - 8, 2)
-        CI.put_point(ab64, m64, loc, 3, rs.uniform(-80, 80, 2))
-        t = time.perf_counter()
-        cm.net_forward(ab64, m64)
-        t1 = time.perf_counter()
-        cd.net_forward(ab64, m64)
-        cd.get_ab_reccs(int(loc[0]), int(loc[1]), K=9)
-        t2 = time.perf_counter()
-        t_col.append((t1 - t) * 1e3); t_all.append((t2 - t) * 1e3)
-    lat["wrapper_p50_ms"] = float(np.percentile(t_col[5:], 50))
-    lat["wrapper_p99_ms"] = float(np.percentile(t_col[5:], 99))
-    lat["wrapper_with_dist_reccs_p50_ms"] = float(np.percentile(t_all[5:], 50))
+
+    def pair(shared):
+        with contextlib.redirect_stdout(io.StringIO()):
+            cm = CI.ColorizeImageB200(Xd=X, maskcent=True)
+            cm.prep_net(state_dict=sd, dist=shared)
+            cd = CI.ColorizeImageB200Dist(Xd=X, maskcent=True)
+            if shared:
+                cd.share_trunk(cm)        # launcher --backend b200: one checkpoint, one trunk (ideepcolor.py:34-38)
+            else:
+                cd.prep_net(state_dict=sd)
+        cm.set_image(img); cd.set_image(img)
+        ab64, m64 = np.zeros((2, X, X)), np.zeros((1, X, X))
+        t_col, t_all = [], []
+        for i in range(25):
+            loc = rs.randint(8, X - 8, 2)
+            CI.put_point(ab64, m64, loc, 3, rs.uniform(-80, 80, 2))
+            t = time.perf_counter()
+            if shared:
+                cd.hint_click(int(loc[0]), int(loc[1]), K=9)
+            cm.net_forward(ab64, m64)
+            t1 = time.perf_counter()
+            cd.net_forward(ab64, m64)
+            cd.get_ab_reccs(int(loc[0]), int(loc[1]), K=9)
+            t2 = time.perf_counter()
+            t_col.append((t1 - t) * 1e3); t_all.append((t2 - t) * 1e3)
+        return t_col[5:], t_all[5:]
+    t_col, t_all = pair(False)
+    lat["wrapper_p50_ms"] = float(np.percentile(t_col, 50))
+    lat["wrapper_p99_ms"] = float(np.percentile(t_col, 99))
+    lat["wrapper_with_dist_reccs_p50_ms"] = float(np.percentile(t_all, 50))
+    _, t_pair = pair(True)
+    lat["wrapper_shared_trunk_with_dist_reccs_p50_ms"] = float(np.percentile(t_pair, 50))
     lat["wrapper_what"] = ("ColorizeImageB200.net_forward(ab, mask) -> uint8 RGB + quantised output_ab (float64 numpy in/out, one "
                            "C-ABI call); with_dist_reccs adds ColorizeImageB200Dist.net_forward + get_ab_reccs(K=9) on a second "
-                           "context, as ui/gui_draw.py:258-286 calls them")
+                           "context, as ui/gui_draw.py:258-286 calls them; shared_trunk = the launcher's default pairing "
+                           "(ColorizeImageB200Dist.share_trunk + hint_click): the same three calls, ONE forward")
     return lat
 
 

@@ -81,6 +81,7 @@ int idc_create(int device, int max_n, int h, int w, unsigned flags, idc_ctx** ou
  *   "split_pairs"   0 / 1       run the split-K (small batch) launches as CTA pairs
  *   "direct_stores" 0 / 1       per-lane 16-byte stores instead of the warp-transposed ones
  *   "host_pipe"     0 / 1       idc_forward_host: chunked copy/compute overlap for batches >= 8
+ *   "early_ab"      0 / 1       click graph: D2H of the ab map forks off right after the last conv (next to Lab->RGB)
  *   "pdl"           0 / 1       programmatic dependent launch between the kernels of one forward
  *   "side_dist"     0 / 1       batches <= 4: run the dist head (class + softmax) on a side stream / graph branch
  *   "tanh_scale"    110 / 100   regression head scale: tanh * 110 (model.py:175) or the Caffe nets' 100
@@ -139,6 +140,13 @@ int idc_forward_host_q(idc_ctx* ctx, int n, int h, int w, const float* L_mc, con
                        const float* mask, float maskcent, const float* glob, float* out_ab,
                        float* out_dist, uint8_t* out_rgb, double* out_abq);
 
+/* The reference splits a session into `set_image` / `load_image` (the L plane, once per photo:
+ * data/colorize_image.py:68-77, :186-189) and `net_forward(input_ab, input_mask)` (per click, :249).  idc_set_image is
+ * the first half: it uploads the n mean-centred L planes [n,1,h,w] once; idc_forward_host(_q) calls with
+ * L_mc == NULL and the same n then reuse them, so a click moves only the hints (3/4 of the input bytes).
+ * n = 0 or L_mc = NULL forgets the image. */
+int idc_set_image(idc_ctx* ctx, int n, int h, int w, const float* L_mc);
+
 /* Page-locked host memory for the zero-copy click path: when every buffer handed to idc_forward_host(_q) with
  * n <= 4 comes from idc_host_alloc (or is otherwise pinned), the copy nodes of the click graph read / write the caller's
  * memory directly (no staging copy by the CPU); buffers laid out back to back -- [L | ab | mask (| glob)] and
@@ -154,6 +162,16 @@ int idc_host_free(void* p);
  * host memory, or the whole [529, h/4, w/4] plane when y4 < 0. */
 int idc_set_dist_resident(idc_ctx* ctx, int on);
 int idc_fetch_dist(idc_ctx* ctx, int img, int y4, int x4, float* out_host);
+
+/* The click itself (BASELINE config 5; ui/gui_draw.py:126-142 -> predict_color / suggest_color): tell the context
+ * BEFORE the forward which pixel (img, y4, x4) of the (h/4 x w/4) distribution grid the user clicked and how many colour
+ * suggestions K (0 = none) the GUI will ask for.  The next idc_forward_host(_q) with n <= 4 and resident mode on then
+ * also gathers that pixel's 529-bin pmf and clusters it (idc_ab_reccs with the default 8 restarts / 100 iterations /
+ * PyTorch gamut grid) on the dist head's side branch of the click graph -- off the critical path -- and brings the 8 KB
+ * answer back with the same graph launch: idc_fetch_dist / idc_ab_reccs for the same pixel (and K) then return from
+ * pinned host memory without touching the device.  The coordinates live in mapped host memory and are read when the
+ * graph runs, so moving the click never re-captures the graph.  y4 < 0 switches the mode off (one re-capture). */
+int idc_set_click(idc_ctx* ctx, int img, int y4, int x4, int K);
 
 /* Colour suggestions at one pixel of the resident distribution (replaces
  * ColorizeImageTorchDist.get_ab_reccs, data/colorize_image.py:322-354: 25 000 inverse-CDF samples of

@@ -37,10 +37,12 @@ SYMBOLS = [
     ("idc_forward_host", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _c.c_float, _P, _P, _P, _P]),
     ("idc_forward_host_q", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _c.c_float, _P, _P, _P, _P, _P]),
     ("idc_set_option", _c.c_int, [_P, _c.c_char_p, _c.c_int]),
+    ("idc_set_image", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P]),
     ("idc_host_alloc", _P, [_c.c_size_t]),
     ("idc_host_free", _c.c_int, [_P]),
     ("idc_set_dist_resident", _c.c_int, [_P, _c.c_int]),
     ("idc_fetch_dist", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _P]),
+    ("idc_set_click", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     ("idc_ab_reccs", _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     ("idc_ab_reccs_pmf", _c.c_int, [_c.c_int, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     ("idc_caffe313_pred_ab", _c.c_int, [_P, _c.c_int, _c.c_float, _P, _P]),

@@ -205,25 +205,26 @@ class ColorizeImageB200(ColorizeImageBase):
         """Stage the reference's float64 arrays into the context's page-locked click buffers (the float64 -> float32
         conversion IS the only CPU copy; L is re-staged only when the image changed), run idc_forward_host_q with
         the pinned buffers (zero-copy graph path) and publish copies of the results as the reference's attributes."""
-        buf = getattr(ctx, "_wrapper_click", None)
-        if buf is None or (glob is not None) != (buf["glob"] is not None):
-            buf = ctx.click_buffers(1, glob=glob is not None)
-            ctx._wrapper_click = buf
-            ctx._wrapper_staged_l = None
-        if ctx._wrapper_staged_l is not self.img_l_mc:
-            np.copyto(buf["L_mc"][0], self.img_l_mc, casting='unsafe')
-            ctx._wrapper_staged_l = self.img_l_mc
-        np.copyto(buf["ab"][0], self.input_ab_mc, casting='unsafe')
-        if mask_div == 1.0:
-            np.copyto(buf["mask"][0], self.input_mask_mult, casting='unsafe')
-        else:
-            np.divide(self.input_mask_mult, mask_div, out=buf["mask"][0], casting='unsafe')
-        if glob is not None:
-            buf["glob"][...] = glob
+        buf = self._click_buffers(ctx, glob is not None)
         want_q = bool(want_rgb and self.gpu_prepost)
-        r = ctx.forward_host(buf["L_mc"], buf["ab"], buf["mask"], maskcent, glob=buf["glob"], want_rgb=want_rgb,
-                             want_abq=want_q, out_ab=buf["out_ab"], out_rgb=buf["out_rgb"] if want_rgb else None,
-                             out_abq=buf["out_abq"] if want_q else None)
+        if ctx._wrapper_shared and glob is None and self._same_as_last_forward(ctx, buf, maskcent, mask_div, want_rgb, want_q):
+            # share_trunk: the other model of the pair just ran this very forward; its results are still in the buffers
+            r = {"ab": buf["out_ab"], "rgb": buf["out_rgb"], "abq": buf["out_abq"]}
+        else:
+            self._stage_image(ctx, buf)
+            np.copyto(buf["ab"][0], self.input_ab_mc, casting='unsafe')
+            if mask_div == 1.0:
+                np.copyto(buf["mask"][0], self.input_mask_mult, casting='unsafe')
+            else:
+                np.divide(self.input_mask_mult, mask_div, out=buf["mask"][0], casting='unsafe')
+            if glob is not None:
+                buf["glob"][...] = glob
+            ctx._wrapper_last = None
+            # L_mc = None: the image uploaded by _stage_image (idc_set_image) -- a click moves only the hints
+            r = ctx.forward_host(None, buf["ab"], buf["mask"], maskcent, glob=buf["glob"], want_rgb=want_rgb,
+                                 want_abq=want_q, out_ab=buf["out_ab"], out_rgb=buf["out_rgb"] if want_rgb else None,
+                                 out_abq=buf["out_abq"] if want_q else None)
+            ctx._wrapper_last = (float(maskcent), float(mask_div), glob is not None, bool(want_rgb), want_q)
         self.output_ab_raw = r["ab"][0].copy()   # raw net output (the parity quantity, SURVEY q2)
         if want_rgb:
             self.output_rgb = r["rgb"][0].copy()
@@ -233,6 +234,49 @@ class ColorizeImageB200(ColorizeImageBase):
             else:
                 ColorizeImageBase._set_out_ab_(self)
         return r
+
+    @staticmethod
+    def _click_buffers(ctx, with_glob):
+        buf = getattr(ctx, "_wrapper_click", None)
+        if buf is None or with_glob != (buf["glob"] is not None):
+            buf = ctx.click_buffers(1, glob=with_glob)
+            ctx._wrapper_click = buf
+            ctx._wrapper_staged_l = []
+            ctx._wrapper_last = None
+        return buf
+
+    def _same_as_last_forward(self, ctx, buf, maskcent, mask_div, want_rgb, want_q):
+        """Did the (shared) context just run exactly this image + these hints (float32, as staged), producing at least
+        the outputs asked for?"""
+        last = ctx._wrapper_last
+        if last is None or last[:3] != (float(maskcent), float(mask_div), False) or (want_rgb and not last[3]) or \
+                (want_q and not last[4]):
+            return False
+        if not any(a is self.img_l_mc for a in ctx._wrapper_staged_l):
+            l32 = np.ascontiguousarray(self.img_l_mc, dtype=np.float32).reshape(buf["L_mc"].shape)
+            if not (ctx._wrapper_staged_l and np.array_equal(buf["L_mc"], l32)):
+                return False
+            ctx._wrapper_staged_l = ctx._wrapper_staged_l[-3:] + [self.img_l_mc]
+        mask32 = np.asarray(self.input_mask_mult, dtype=np.float32)
+        if mask_div != 1.0:
+            mask32 = mask32 / np.float32(mask_div)
+        return (np.array_equal(buf["ab"][0], np.asarray(self.input_ab_mc, dtype=np.float32)) and
+                np.array_equal(buf["mask"][0], mask32))
+
+    def _stage_image(self, ctx, buf):
+        """The L plane goes to the device once per image (reference: set_image / load_image, :68-77), not once per
+        click.  `_wrapper_staged_l` lists the img_l_mc arrays known to equal the resident plane (several wrapper
+        objects may share one context, see ColorizeImageB200Dist.share_trunk)."""
+        if any(a is self.img_l_mc for a in ctx._wrapper_staged_l):
+            return
+        l32 = np.ascontiguousarray(self.img_l_mc, dtype=np.float32).reshape(buf["L_mc"].shape)
+        if ctx._wrapper_staged_l and np.array_equal(buf["L_mc"], l32):
+            ctx._wrapper_staged_l = ctx._wrapper_staged_l[-3:] + [self.img_l_mc]
+            return
+        buf["L_mc"][...] = l32
+        ctx.set_image(buf["L_mc"])
+        ctx._wrapper_staged_l = [self.img_l_mc]
+        ctx._wrapper_last = None
 
     @property
     def output_lab(self):
@@ -351,6 +395,38 @@ class ColorizeImageB200Dist(ColorizeImageB200):
     def prep_net(self, gpu_id=None, path='', dist=True, S=.2, state_dict=None):
         ColorizeImageB200.prep_net(self, gpu_id=gpu_id, path=path, dist=dist, state_dict=state_dict)
 
+    def share_trunk(self, color_model):
+        """ONE forward per click instead of two.  The PyTorch backend loads the same checkpoint into both models
+        (ideepcolor.py:34-38 "same model used for both") and the GUI feeds both the same hints, one after the other
+        (ui/gui_draw.py:250-258 predict_color, :272-279 compute_result); the distribution head hangs off conv8_3 of
+        the very trunk the colour model just ran.  After `share_trunk(color_model)` -- color_model prepared with
+        `prep_net(..., dist=True)` -- this object uses the colour model's network: when net_forward sees the image and
+        hints the shared context ran last, it publishes that forward's outputs (the resident distribution, the raw ab
+        map) without launching anything; otherwise it runs the forward itself -- and the colour model's next
+        net_forward with the same hints is answered from THAT forward (the sharing is symmetric, whichever model the
+        GUI calls first pays).  Replaces prep_net."""
+        net = getattr(color_model, "net", None)
+        if not getattr(color_model, "net_set", False) or net is None or not getattr(net, "dist", False):
+            raise ValueError("share_trunk: prepare the colour model with prep_net(..., dist=True) first")
+        self.net = net
+        self.net_set = True
+        self._trunk = color_model
+        Xd = self.Xd
+        ctx = net._context(Xd, Xd, 1)
+        ctx.set_dist_resident(True)          # every forward of the shared context keeps its distribution
+        ctx._wrapper_shared = True           # _click may now answer from the other model's forward
+        return self
+
+    def hint_click(self, h, w, K=9):
+        """Announce the pixel the GUI is about to ask suggestions for (ui/gui_draw.py:184 `suggest_color(h=y, w=x, K=9)`)
+        BEFORE the forward: its pmf and the K suggestions then come back with the click itself (idc_set_click), and
+        `dist_ab[:, h, w]` / `get_ab_reccs(h, w, K)` cost no device work.  h = None switches it off."""
+        ctx = self.net._context(self.Xd, self.Xd, 1)
+        if h is None:
+            ctx.set_click(0, -1, 0, 0)
+        else:
+            ctx.set_click(0, int(h) // 4, int(w) // 4, int(K))
+
     def net_forward(self, input_ab, input_mask):
         if ColorizeImageBase.net_forward(self, input_ab, input_mask) == -1:
             return -1
@@ -365,7 +441,8 @@ class ColorizeImageB200Dist(ColorizeImageB200):
             self.output_ab_raw = r["ab"][0]
         else:
             ctx.set_dist_resident(True)                      # dist stays in HBM; pixels are fetched on demand
-            self._click(ctx, float(self.mask_cent), want_rgb=False)
+            # on a shared context keep the colour model's graph (same outputs requested -> no re-capture)
+            self._click(ctx, float(self.mask_cent), want_rgb=getattr(self, "_trunk", None) is not None)
         if self.materialize_full:
             self.dist_ab = np.repeat(np.repeat(self.dist_ab_64, 4, axis=1), 4, axis=2)
             self.dist_ab_full = np.zeros((self.AB, self.Xd, self.Xd))

@@ -487,11 +487,34 @@ struct HostPipe {
   float* ab_dst = nullptr;    // pinned host destination of out_ab (caller's buffer or the staging block)
 };
 
+// idc_set_click: layout of the click answer block (device d_clickout, pinned host h_clickout)
+constexpr int kClickInit = 8, kClickMaxIter = 100;                       // the defaults of LhnContext.ab_reccs
+constexpr size_t kClickHdr = 32, kClickPmf = 544 * sizeof(float);
+constexpr size_t kClickRes = (size_t)kClickInit * (3 * 32 + 2) * sizeof(double);
+constexpr size_t kClickCopy = kClickHdr + kClickPmf + kClickRes;         // what travels back per click
+constexpr size_t kClickBytes = kClickCopy + 529 * 2 * sizeof(float);     // + the default gamut grid (device only)
+
+// After the softmax of a small-batch forward: gather the clicked pixel's pmf, cluster it (K from the click header),
+// copy the block to pinned host memory.  Runs on the dist head's stream, i.e. off the critical path of the click.
+cudaError_t click_tail(Ctx* c, int n, const float* dist, cudaStream_t st) {
+  if (!c->click_mode || !c->d_clickout || n > 4) return cudaSuccess;
+  int* hdr = reinterpret_cast<int*>(c->d_clickout);
+  float* pmf = reinterpret_cast<float*>(c->d_clickout + kClickHdr);
+  double* res = reinterpret_cast<double*>(c->d_clickout + kClickHdr + kClickPmf);
+  const float* pts = reinterpret_cast<const float*>(c->d_clickout + kClickCopy);
+  cudaError_t e = launch_click_pmf(dist, c->d_click, n, c->H / 4, c->W / 4, hdr, pmf, st);
+  if (e != cudaSuccess) return e;
+  if ((e = launch_ab_reccs(pmf, 1, pts, 0, kClickMaxIter, kClickInit, res, st, hdr)) != cudaSuccess) return e;
+  c->launch_count += 2;
+  return cudaMemcpyAsync(c->h_clickout, c->d_clickout, kClickCopy, cudaMemcpyDeviceToHost, st);
+}
+
 int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mask, float maskcent, const float* glob,
                 float* out_ab, float* out_dist, uint8_t* out_rgb, cudaStream_t st, const HostPipe* hp = nullptr,
                 double* out_abq = nullptr) {
   c->launch_count = 0;
   c->gadd_active = false;
+  c->click_served = false;
   pdl_break(c);                        // whatever precedes this forward on `st` is not one of its kernels
   std::vector<cudaEvent_t>* ev = nullptr;
   auto mark = [&]() {
@@ -525,7 +548,7 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
   // 9-10 do not depend on it -> it runs on a side stream (a parallel branch of the click graph) on the ~20 SMs the
   // 128-CTA launches of the main chain leave idle, instead of sitting between c8_3 and up9 on the critical path.
   const bool side_dist = c->opt.side_dist && !c->simt && out_dist && n <= 4 && !hp && !ev;
-  bool forked = false;
+  bool forked = false, ab_forked = false;
   for (auto& op : c->ops) {
     if (side_dist && op.kind == OP_CLASS && op.name == "class") {
       if (!c->s_side) {
@@ -541,6 +564,7 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
       pdl_break(c);                                        // first kernel of the branch follows an event wait
       CUDA_TRY(c, umma_run_op(c, op, n, nullptr, (float)c->opt.tanh_scale, c->s_side, 0, 16));
       CUDA_TRY(c, launch_softmax529(c, n, out_dist, c->s_side));     // PDL-chained behind `class` on the side stream
+      CUDA_TRY(c, click_tail(c, n, out_dist, c->s_side));            // idc_set_click: clicked pixel's pmf + suggestions
       CUDA_TRY(c, cudaEventRecord(c->ev_join, c->s_side));
       // in a capture the event record is not a node: up9 keeps its programmatic edge to c8_3; on a live stream the
       // record sits between the two kernels, so the next launch is serialised normally
@@ -562,18 +586,42 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
       }
     } else {
       CUDA_TRY(c, umma_run_op(c, op, n, op.fuse_out_head ? out_ab : nullptr, (float)c->opt.tanh_scale, st));
+      if (op.fuse_out_head && c->ab_early_dst) {
+        // click graph: the D2H of the ab map starts as soon as the last conv is done, next to the Lab->RGB kernel
+        if (!c->s_ab) {
+          CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_ab, cudaStreamNonBlocking));
+          CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_ab[0], cudaEventDisableTiming));
+          CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_ab[1], cudaEventDisableTiming));
+        }
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        CUDA_TRY(c, cudaStreamIsCapturing(st, &cap));
+        CUDA_TRY(c, cudaEventRecord(c->ev_ab[0], st));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->s_ab, c->ev_ab[0], 0));
+        CUDA_TRY(c, cudaMemcpyAsync(c->ab_early_dst, out_ab, (size_t)n * 2 * HW * sizeof(float), cudaMemcpyDeviceToHost, c->s_ab));
+        CUDA_TRY(c, cudaEventRecord(c->ev_ab[1], c->s_ab));
+        if (cap != cudaStreamCaptureStatusActive) pdl_break(c);   // live stream: the record sits between the two kernels
+        ab_forked = true;
+      }
     }
     mark();
   }
   const bool fused = !c->simt && !(c->flags & IDC_FLAG_KEEP_CONV10);
   if (!fused) CUDA_TRY(c, launch_out_head(c, n, out_ab, st));
-  if (out_dist && !forked) CUDA_TRY(c, launch_softmax529(c, n, out_dist, st));
+  if (out_dist && !forked) {
+    CUDA_TRY(c, launch_softmax529(c, n, out_dist, st));
+    CUDA_TRY(c, click_tail(c, n, out_dist, st));
+    pdl_break(c);
+  }
   if (out_rgb) {
     CUDA_TRY(c, launch_lab2rgb(c, n, c->H, c->W, L, 50.0f, out_ab, out_rgb, st, out_abq));
     c->launch_count++;
   }
   if (forked) {
     CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_join, 0));   // join: whatever follows on `st` sees the distribution
+    pdl_break(c);
+  }
+  if (ab_forked) {
+    CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_ab[1], 0));
     pdl_break(c);
   }
   mark();
@@ -587,7 +635,7 @@ int check_forward_args(Ctx* c, int n, int h, int w, const void* L, const void* a
   if (!c->weights_ready) return fail(c, IDC_ERR_STATE, "idc_forward before idc_finalize_weights");
   if (n < 1 || n > c->max_n) return fail(c, IDC_ERR_ARG, "n=%d outside [1,%d]", n, c->max_n);
   if (h != c->H || w != c->W) return fail(c, IDC_ERR_ARG, "geometry %dx%d != ctx geometry %dx%d", h, w, c->H, c->W);
-  if (!L || !ab || !mask || !out_ab) return fail(c, IDC_ERR_ARG, "null L/ab/mask/out_ab");
+  if (!L || !ab || !mask || !out_ab) return fail(c, IDC_ERR_ARG, "null L/ab/mask/out_ab");   // L: see idc_set_image
   if (out_dist && !c->dist) return fail(c, IDC_ERR_ARG, "out_dist requires IDC_FLAG_DIST");
   if (glob && !c->glob) return fail(c, IDC_ERR_ARG, "glob requires IDC_FLAG_GLOBAL_HINTS");
   return IDC_OK;
@@ -635,11 +683,11 @@ int idc_set_option(idc_ctx* c, const char* name, int value) {
       {"halo", &c->opt.halo}, {"pairs", &c->opt.pairs}, {"mt", &c->opt.mt}, {"chunk_kb", &c->opt.chunk_kb},
       {"split_k", &c->opt.split_k}, {"direct_stores", &c->opt.direct_stores}, {"host_pipe", &c->opt.host_pipe},
       {"pdl", &c->opt.pdl}, {"split_pairs", &c->opt.split_pairs}, {"tanh_scale", &c->opt.tanh_scale},
-      {"side_dist", &c->opt.side_dist}, {"split_bn128", &c->opt.split_bn128}};
+      {"side_dist", &c->opt.side_dist}, {"split_bn128", &c->opt.split_bn128}, {"early_ab", &c->opt.early_ab}};
   for (auto& t : tab)
     if (!strcmp(t.n, name)) {
       *t.v = value;
-      if (c->weights_ready && strcmp(name, "host_pipe") && strcmp(name, "tanh_scale") && strcmp(name, "side_dist")) {      // plan-time option changed after planning: re-plan
+      if (c->weights_ready && strcmp(name, "host_pipe") && strcmp(name, "tanh_scale") && strcmp(name, "side_dist") && strcmp(name, "early_ab")) {      // plan-time option changed after planning: re-plan
         CUDA_TRY(c, cudaSetDevice(c->dev));
         CUDA_TRY(c, cudaDeviceSynchronize());
         int rc = plan_engines(c);
@@ -768,20 +816,23 @@ static int forward_host_small(idc_ctx* c, int n, const float* L, const float* ab
   float* ddist = c->d_out + (size_t)c->max_n * 2 * HW;
   const size_t out_bytes = b_ab + (want_rgb ? b_rgb : 0) + (want_q ? b_q : 0);
   const uintptr_t flags = (uintptr_t)n | ((uintptr_t)want_dist << 8) | ((uintptr_t)want_rgb << 9) | ((uintptr_t)want_glob << 10) |
-                          ((uintptr_t)want_q << 11) | ((uintptr_t)copy_dist << 12);
+                          ((uintptr_t)want_q << 11) | ((uintptr_t)copy_dist << 12) | ((uintptr_t)c->click_mode << 13);
+  c->click_served = false;
+  const bool have_L = L != nullptr;          // false: the image set by idc_set_image stays where it is
+  const size_t in_floats = (size_t)n * (have_L ? 4 : 3) * HW + (want_glob ? (size_t)n * 316 : 0);
   const void* direct_key[8] = {(void*)(flags | (1u << 16)), L, ab, mask, glob, out_ab, out_rgb, out_abq};
   // fast path: same pinned buffers as the captured graph -> replay without touching the driver's pointer tables
   bool direct = c->graph_exec && !copy_dist && memcmp(direct_key, c->graph_ptrs, sizeof(direct_key)) == 0 &&
                 c->graph_maskcent == maskcent;
   bool replay = direct;
   if (!direct) {
-    direct = !copy_dist && is_pinned(L) && is_pinned(ab) && is_pinned(mask) && (!glob || is_pinned(glob)) &&
+    direct = !copy_dist && (!have_L || is_pinned(L)) && is_pinned(ab) && is_pinned(mask) && (!glob || is_pinned(glob)) &&
              is_pinned(out_ab) && (!out_rgb || is_pinned(out_rgb)) && (!out_abq || is_pinned(out_abq));
   }
-  const void* staged_key[8] = {(void*)flags, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const void* staged_key[8] = {(void*)(flags | ((uintptr_t)have_L << 17)), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   const void** key = direct ? direct_key : staged_key;
   if (!direct) {   // stage the inputs
-    memcpy(c->h_in, L, (size_t)n * HW * sizeof(float));
+    if (have_L) memcpy(c->h_in, L, (size_t)n * HW * sizeof(float));
     memcpy(c->h_in + (size_t)n * HW, ab, (size_t)n * 2 * HW * sizeof(float));
     memcpy(c->h_in + (size_t)n * 3 * HW, mask, (size_t)n * HW * sizeof(float));
     if (want_glob) memcpy(c->h_in + (size_t)n * 4 * HW, glob, (size_t)n * 316 * sizeof(float));
@@ -797,37 +848,43 @@ static int forward_host_small(idc_ctx* c, int n, const float* L, const float* ab
       if (ce == cudaSuccess && bytes) ce = cudaMemcpyAsync(dst, src, bytes, kind, st);
     };
     if (direct) {
-      const bool contig = ab == L + (size_t)n * HW && mask == ab + (size_t)n * 2 * HW &&
+      const bool contig = (!have_L || ab == L + (size_t)n * HW) && mask == ab + (size_t)n * 2 * HW &&
                           (!want_glob || glob == mask + (size_t)n * HW);
       if (contig) {
-        cp(dL, L, ((size_t)n * 4 * HW + (want_glob ? (size_t)n * 316 : 0)) * sizeof(float), cudaMemcpyHostToDevice);
+        cp(have_L ? dL : dab, have_L ? L : ab, in_floats * sizeof(float), cudaMemcpyHostToDevice);
       } else {
-        cp(dL, L, (size_t)n * HW * sizeof(float), cudaMemcpyHostToDevice);
+        if (have_L) cp(dL, L, (size_t)n * HW * sizeof(float), cudaMemcpyHostToDevice);
         cp(dab, ab, (size_t)n * 2 * HW * sizeof(float), cudaMemcpyHostToDevice);
         cp(dmask, mask, (size_t)n * HW * sizeof(float), cudaMemcpyHostToDevice);
         if (want_glob) cp(dglob, glob, (size_t)n * 316 * sizeof(float), cudaMemcpyHostToDevice);
       }
     } else {
-      cp(c->d_in, c->h_in, ((size_t)n * 4 * HW + (want_glob ? (size_t)n * 316 : 0)) * sizeof(float), cudaMemcpyHostToDevice);
+      const size_t off = have_L ? 0 : (size_t)n * HW;
+      cp(c->d_in + off, c->h_in + off, in_floats * sizeof(float), cudaMemcpyHostToDevice);
     }
     int rc = IDC_OK;
+    // with an RGB post-process behind it, the D2H of the ab map forks off right after the last conv
+    const bool early_ab = want_rgb && c->opt.early_ab;
+    c->ab_early_dst = early_ab ? (direct ? out_ab : reinterpret_cast<float*>(hsm)) : nullptr;
     if (ce == cudaSuccess)
       rc = run_forward(c, n, dL, dab, dmask, maskcent, want_glob ? dglob : nullptr, dout, want_dist ? ddist : nullptr,
                        want_rgb ? drgb : nullptr, st, nullptr, want_q ? dq : nullptr);
+    c->ab_early_dst = nullptr;
     if (rc == IDC_OK) {
       if (direct) {
         const char* o0 = reinterpret_cast<const char*>(out_ab);
         const bool contig = (!want_rgb || reinterpret_cast<const char*>(out_rgb) == o0 + b_ab) &&
                             (!want_q || reinterpret_cast<const char*>(out_abq) == o0 + b_ab + b_rgb);
         if (contig) {
-          cp(out_ab, dsm, out_bytes, cudaMemcpyDeviceToHost);
+          cp(reinterpret_cast<char*>(out_ab) + (early_ab ? b_ab : 0), dsm + (early_ab ? b_ab : 0),
+             out_bytes - (early_ab ? b_ab : 0), cudaMemcpyDeviceToHost);
         } else {
-          cp(out_ab, dout, b_ab, cudaMemcpyDeviceToHost);
+          if (!early_ab) cp(out_ab, dout, b_ab, cudaMemcpyDeviceToHost);
           if (want_rgb) cp(out_rgb, drgb, b_rgb, cudaMemcpyDeviceToHost);
           if (want_q) cp(out_abq, dq, b_q, cudaMemcpyDeviceToHost);
         }
       } else {
-        cp(hsm, dsm, out_bytes, cudaMemcpyDeviceToHost);
+        cp(hsm + (early_ab ? b_ab : 0), dsm + (early_ab ? b_ab : 0), out_bytes - (early_ab ? b_ab : 0), cudaMemcpyDeviceToHost);
         if (copy_dist)
           cp(c->h_out + (size_t)c->max_n * 2 * HW, ddist, (size_t)n * 529 * HW4 * sizeof(float), cudaMemcpyDeviceToHost);
       }
@@ -858,6 +915,42 @@ static int forward_host_small(idc_ctx* c, int n, const float* L, const float* ab
     if (copy_dist) memcpy(out_dist, c->h_out + (size_t)c->max_n * 2 * HW, (size_t)n * 529 * HW4 * sizeof(float));
   }
   c->dist_valid_n = want_dist ? n : 0;
+  c->click_served = want_dist && c->click_mode && c->h_clickout;     // the side branch delivered the click's answer
+  if (have_L) c->image_n = n;          // the planes just uploaded are the resident image now
+  return IDC_OK;
+}
+
+static int ensure_host_staging(idc_ctx* c) {
+  if (c->d_in) return IDC_OK;
+  const size_t HW = (size_t)c->H * c->W, HW4 = (size_t)(c->H / 4) * (c->W / 4);
+  const int small_n = c->max_n < 4 ? c->max_n : 4;
+  c->in_floats = (size_t)c->max_n * (4 * HW + 316);
+  c->out_floats = (size_t)c->max_n * (2 * HW + (c->dist ? 529 * HW4 : 0));
+  const size_t small_bytes = (size_t)small_n * (2 * HW * 4 + 3 * HW + 2 * HW * 8);
+  CUDA_TRY(c, cudaMalloc(&c->d_in, c->in_floats * sizeof(float)));
+  CUDA_TRY(c, cudaMalloc(&c->d_out, c->out_floats * sizeof(float)));
+  CUDA_TRY(c, cudaMalloc(&c->d_rgb, (size_t)c->max_n * HW * 3));
+  CUDA_TRY(c, cudaMalloc(&c->d_small, small_bytes));
+  CUDA_TRY(c, cudaMallocHost(&c->h_in, c->in_floats * sizeof(float)));
+  CUDA_TRY(c, cudaMallocHost(&c->h_out, c->out_floats * sizeof(float)));
+  CUDA_TRY(c, cudaMallocHost(&c->h_rgb, (size_t)c->max_n * HW * 3));
+  CUDA_TRY(c, cudaMallocHost(&c->h_small, small_bytes));
+  return IDC_OK;
+}
+
+int idc_set_image(idc_ctx* c, int n, int h, int w, const float* L) {
+  if (!c) return IDC_ERR_ARG;
+  if (n < 0 || n > c->max_n) return fail(c, IDC_ERR_ARG, "n=%d outside [0,%d]", n, c->max_n);
+  if (n == 0 || !L) { c->image_n = 0; return IDC_OK; }
+  if (h != c->H || w != c->W) return fail(c, IDC_ERR_ARG, "geometry %dx%d != ctx geometry %dx%d", h, w, c->H, c->W);
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  int rc = ensure_host_staging(c);
+  if (rc != IDC_OK) return rc;
+  c->image_n = 0;
+  CUDA_TRY(c, cudaStreamSynchronize(c->own_stream));
+  // the L planes sit at the head of the input block for every batch size (small and large path alike)
+  CUDA_TRY(c, cudaMemcpy(c->d_in, L, (size_t)n * c->H * c->W * sizeof(float), cudaMemcpyHostToDevice));
+  c->image_n = n;
   return IDC_OK;
 }
 
@@ -865,7 +958,7 @@ int idc_forward_host_q(idc_ctx* c, int n, int h, int w, const float* L, const fl
                        float maskcent, const float* glob, float* out_ab, float* out_dist, uint8_t* out_rgb,
                        double* out_abq) {
   if (!c) return IDC_ERR_ARG;
-  int rc = check_forward_args(c, n, h, w, L, ab, mask, glob, out_ab, out_dist);
+  int rc = check_forward_args(c, n, h, w, L ? (const void*)L : (const void*)c, ab, mask, glob, out_ab, out_dist);
   if (rc != IDC_OK) return rc;
   if (out_abq && !out_rgb) return fail(c, IDC_ERR_ARG, "out_abq (quantised ab) is derived from out_rgb: pass both");
   CUDA_TRY(c, cudaSetDevice(c->dev));
@@ -874,20 +967,10 @@ int idc_forward_host_q(idc_ctx* c, int n, int h, int w, const float* L, const fl
     return fail(c, IDC_ERR_WATCHDOG, "device pipeline watchdog fired earlier (code %d)", werr);
   }
   const size_t HW = (size_t)c->H * c->W, HW4 = (size_t)(c->H / 4) * (c->W / 4);
-  const int small_n = c->max_n < 4 ? c->max_n : 4;
-  if (!c->d_in) {
-    c->in_floats = (size_t)c->max_n * (4 * HW + 316);
-    c->out_floats = (size_t)c->max_n * (2 * HW + (c->dist ? 529 * HW4 : 0));
-    const size_t small_bytes = (size_t)small_n * (2 * HW * 4 + 3 * HW + 2 * HW * 8);
-    CUDA_TRY(c, cudaMalloc(&c->d_in, c->in_floats * sizeof(float)));
-    CUDA_TRY(c, cudaMalloc(&c->d_out, c->out_floats * sizeof(float)));
-    CUDA_TRY(c, cudaMalloc(&c->d_rgb, (size_t)c->max_n * HW * 3));
-    CUDA_TRY(c, cudaMalloc(&c->d_small, small_bytes));
-    CUDA_TRY(c, cudaMallocHost(&c->h_in, c->in_floats * sizeof(float)));
-    CUDA_TRY(c, cudaMallocHost(&c->h_out, c->out_floats * sizeof(float)));
-    CUDA_TRY(c, cudaMallocHost(&c->h_rgb, (size_t)c->max_n * HW * 3));
-    CUDA_TRY(c, cudaMallocHost(&c->h_small, small_bytes));
-  }
+  rc = ensure_host_staging(c);
+  if (rc != IDC_OK) return rc;
+  if (!L && c->image_n != n)
+    return fail(c, IDC_ERR_STATE, "L_mc is NULL but no %d-image set is resident (idc_set_image)", n);
   const bool use_graph = !(c->flags & IDC_FLAG_NO_GRAPH) && n <= 4;
   if (use_graph) {
     rc = forward_host_small(c, n, L, ab, mask, maskcent, glob, out_ab, out_dist, out_rgb, out_abq);
@@ -940,14 +1023,14 @@ int idc_forward_host_q(idc_ctx* c, int n, int h, int w, const float* L, const fl
     if (glob) CUDA_TRY(c, h2d(dglob, glob, (size_t)n * 316, (size_t)c->max_n * 4 * HW));
     for (int k = 0; k < hp.nchunks; ++k) {
       const size_t i0 = hp.start[k], nk = hp.start[k + 1] - hp.start[k];
-      CUDA_TRY(c, h2d(dL + i0 * HW, L + i0 * HW, nk * HW, i0 * HW));
+      if (L) CUDA_TRY(c, h2d(dL + i0 * HW, L + i0 * HW, nk * HW, i0 * HW));
       CUDA_TRY(c, h2d(dab + i0 * 2 * HW, ab + i0 * 2 * HW, nk * 2 * HW, (size_t)c->max_n * HW + i0 * 2 * HW));
       CUDA_TRY(c, h2d(dmask + i0 * HW, mask + i0 * HW, nk * HW, (size_t)c->max_n * 3 * HW + i0 * HW));
       CUDA_TRY(c, cudaEventRecord(c->ev_in[k], c->s_in));
     }
     st = compute;
   } else {
-    CUDA_TRY(c, h2d(dL, L, n * HW, 0));
+    if (L) CUDA_TRY(c, h2d(dL, L, n * HW, 0));
     CUDA_TRY(c, h2d(dab, ab, n * 2 * HW, (size_t)c->max_n * HW));
     CUDA_TRY(c, h2d(dmask, mask, n * HW, (size_t)c->max_n * 3 * HW));
     if (glob) CUDA_TRY(c, h2d(dglob, glob, (size_t)n * 316, (size_t)c->max_n * 4 * HW));
@@ -969,6 +1052,7 @@ int idc_forward_host_q(idc_ctx* c, int n, int h, int w, const float* L, const fl
   if (out_abq) CUDA_TRY(c, d2h(out_abq, c->d_abq, n * 2 * HW * sizeof(double), c->h_abq));
   CUDA_TRY(c, cudaStreamSynchronize(st));
   if (hp.nchunks) CUDA_TRY(c, cudaStreamSynchronize(c->s_out));
+  if (L) c->image_n = n;
   if (!is_pinned(out_ab)) memcpy(out_ab, c->h_out, n * 2 * HW * sizeof(float));
   if (copy_dist && !is_pinned(out_dist)) memcpy(out_dist, c->h_out + (size_t)c->max_n * 2 * HW, n * 529 * HW4 * sizeof(float));
   c->dist_valid_n = want_dist ? n : 0;
@@ -999,6 +1083,38 @@ int idc_set_dist_resident(idc_ctx* c, int on) {
   return IDC_OK;
 }
 
+// does the pinned click block hold the answer for this pixel?
+static bool click_answers(idc_ctx* c, int img, int y4, int x4) {
+  if (!c->click_served || !c->h_clickout) return false;
+  const int* hdr = reinterpret_cast<const int*>(c->h_clickout);
+  return hdr[7] == 1 && hdr[0] == img && hdr[1] == y4 && hdr[2] == x4;
+}
+
+int idc_set_click(idc_ctx* c, int img, int y4, int x4, int K) {
+  if (!c) return IDC_ERR_ARG;
+  if (!c->dist) return fail(c, IDC_ERR_ARG, "idc_set_click requires IDC_FLAG_DIST");
+  if (K < 0 || K > 32) return fail(c, IDC_ERR_ARG, "idc_set_click: need 0 <= K <= 32");
+  CUDA_TRY(c, cudaSetDevice(c->dev));
+  if (!c->h_click) {
+    CUDA_TRY(c, cudaHostAlloc(&c->h_click, 64, cudaHostAllocMapped));
+    memset(c->h_click, 0, 64);
+    c->h_click[1] = -1;
+    CUDA_TRY(c, cudaHostGetDevicePointer(&c->d_click, c->h_click, 0));
+    CUDA_TRY(c, cudaMalloc(&c->d_clickout, kClickBytes));
+    CUDA_TRY(c, cudaMemset(c->d_clickout, 0, kClickBytes));
+    CUDA_TRY(c, cudaMallocHost(&c->h_clickout, kClickCopy));
+    memset(c->h_clickout, 0, kClickCopy);
+    float pts[529 * 2];   // the PyTorch wrapper's gamut grid (data/colorize_image.py:283): bin i = (g[i % 23], g[i / 23])
+    for (int i = 0; i < 529; ++i) { pts[2 * i] = -110.f + 10.f * (i % 23); pts[2 * i + 1] = -110.f + 10.f * (i / 23); }
+    CUDA_TRY(c, cudaMemcpy(c->d_clickout + kClickCopy, pts, sizeof(pts), cudaMemcpyHostToDevice));
+  }
+  volatile int* h = c->h_click;
+  h[0] = img; h[1] = y4; h[2] = x4; h[3] = K; h[4] = h[4] + 1;
+  c->click_mode = y4 >= 0;           // part of the graph key: switching the mode re-captures the click graph once
+  c->click_served = false;
+  return IDC_OK;
+}
+
 int idc_fetch_dist(idc_ctx* c, int img, int y4, int x4, float* out) {
   if (!c || !out) return IDC_ERR_ARG;
   if (img < 0 || img >= c->dist_valid_n || !c->d_out)
@@ -1012,6 +1128,10 @@ int idc_fetch_dist(idc_ctx* c, int img, int y4, int x4, float* out) {
     return IDC_OK;
   }
   if (y4 >= H4 || x4 < 0 || x4 >= W4) return fail(c, IDC_ERR_ARG, "pixel (%d,%d) outside the %dx%d grid", y4, x4, H4, W4);
+  if (click_answers(c, img, y4, x4)) {       // idc_set_click: the forward already brought this pixel back
+    memcpy(out, c->h_clickout + kClickHdr, 529 * sizeof(float));
+    return IDC_OK;
+  }
   // one float per bin, bins are HW4 floats apart (NCHW)
   CUDA_TRY(c, cudaMemcpy2D(out, sizeof(float), d + (size_t)y4 * W4 + x4, HW4 * sizeof(float), sizeof(float), 529,
                            cudaMemcpyDeviceToHost));
@@ -1025,6 +1145,19 @@ constexpr size_t kReccsScratchBytes = (size_t)kReccsMaxInit * kReccsRes * sizeof
 
 static bool reccs_args_ok(int K, int max_iter, int n_init) {
   return K >= 1 && K <= 32 && max_iter >= 1 && n_init >= 1 && n_init <= kReccsMaxInit;
+}
+
+// best restart = lowest inertia; restarts within 1e-9 (relative) of it count as ties -> lowest index
+static void reccs_pick(const double* res, int K, int n_init, float* centers_host, float* conf_host, int* iters_out) {
+  const int stride = 3 * K + 2;
+  double best = res[stride - 1];
+  for (int v = 1; v < n_init; ++v) best = std::min(best, res[v * stride + stride - 1]);
+  int pick = 0;
+  while (res[pick * stride + stride - 1] > best * (1.0 + 1e-9) + 1e-300) ++pick;
+  const double* r = res + (size_t)pick * stride;
+  for (int i = 0; i < 2 * K; ++i) centers_host[i] = (float)r[i];
+  if (conf_host) for (int k = 0; k < K; ++k) conf_host[k] = (float)r[2 * K + k];
+  if (iters_out) *iters_out = (int)r[3 * K];
 }
 
 static cudaError_t reccs_run(const float* pmf_dev, size_t bin_stride, double* scratch, int K, int max_iter, int n_init,
@@ -1042,15 +1175,7 @@ static cudaError_t reccs_run(const float* pmf_dev, size_t bin_stride, double* sc
   const int stride = 3 * K + 2;
   double res[kReccsMaxInit * kReccsRes];
   if ((e = cudaMemcpy(res, scratch, (size_t)n_init * stride * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
-  // best restart = lowest inertia; restarts within 1e-9 (relative) of it count as ties -> lowest index
-  double best = res[stride - 1];
-  for (int v = 1; v < n_init; ++v) best = std::min(best, res[v * stride + stride - 1]);
-  int pick = 0;
-  while (res[pick * stride + stride - 1] > best * (1.0 + 1e-9) + 1e-300) ++pick;
-  const double* r = res + (size_t)pick * stride;
-  for (int i = 0; i < 2 * K; ++i) centers_host[i] = (float)r[i];
-  if (conf_host) for (int k = 0; k < K; ++k) conf_host[k] = (float)r[2 * K + k];
-  if (iters_out) *iters_out = (int)r[3 * K];
+  reccs_pick(res, K, n_init, centers_host, conf_host, iters_out);
   return cudaSuccess;
 }
 
@@ -1064,6 +1189,22 @@ int idc_ab_reccs(idc_ctx* c, int img, int y4, int x4, int K, int max_iter, int n
   const int H4 = c->H / 4, W4 = c->W / 4;
   if (y4 < 0 || y4 >= H4 || x4 < 0 || x4 >= W4) return fail(c, IDC_ERR_ARG, "pixel (%d,%d) outside the %dx%d grid", y4, x4, H4, W4);
   const size_t HW = (size_t)c->H * c->W, HW4 = (size_t)H4 * W4;
+  // idc_set_click with the same pixel and K, default restarts / iterations / gamut grid: the click graph already
+  // clustered this pmf on its side branch and the results are in pinned host memory
+  if (click_answers(c, img, y4, x4) && reinterpret_cast<const int*>(c->h_clickout)[3] == K && max_iter == kClickMaxIter &&
+      n_init == kClickInit) {
+    bool default_pts = pts_host == nullptr;
+    if (!default_pts) {
+      default_pts = true;
+      for (int i = 0; i < 529 && default_pts; ++i)
+        default_pts = pts_host[2 * i] == -110.f + 10.f * (i % 23) && pts_host[2 * i + 1] == -110.f + 10.f * (i / 23);
+    }
+    if (default_pts) {
+      reccs_pick(reinterpret_cast<const double*>(c->h_clickout + kClickHdr + kClickPmf), K, n_init, centers_host, conf_host,
+                 iters_out);
+      return IDC_OK;
+    }
+  }
   const float* d = c->d_out + (size_t)c->max_n * 2 * HW + (size_t)img * 529 * HW4 + (size_t)y4 * W4 + x4;
   CUDA_TRY(c, cudaSetDevice(c->dev));
   if (!c->d_reccs) CUDA_TRY(c, cudaMalloc(&c->d_reccs, kReccsScratchBytes));
@@ -1301,8 +1442,12 @@ int idc_destroy(idc_ctx* c) {
   if (c->h_in) cudaFreeHost(c->h_in);
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_rgb) cudaFreeHost(c->h_rgb);
+  if (c->h_click) cudaFreeHost(c->h_click);
+  if (c->d_clickout) cudaFree(c->d_clickout);
+  if (c->h_clickout) cudaFreeHost(c->h_clickout);
   if (c->dbg_ev[0]) { cudaEventDestroy(c->dbg_ev[0]); cudaEventDestroy(c->dbg_ev[1]); }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->s_ab) { cudaStreamDestroy(c->s_ab); cudaEventDestroy(c->ev_ab[0]); cudaEventDestroy(c->ev_ab[1]); }
   if (c->s_side) { cudaStreamDestroy(c->s_side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
   if (c->s_in) {
     cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);

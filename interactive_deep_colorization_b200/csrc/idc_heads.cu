@@ -659,11 +659,35 @@ __device__ __forceinline__ int block_argmax(double v, int idx, double* rv, int* 
   return r;
 }
 
+// The click of the interactive path (idc_set_click): `click` = {img, y4, x4, K, seq, ...} in mapped host memory, read
+// when the graph RUNS (the graph itself never changes).  Copies dist[img, :, y4, x4] (529 floats) behind an 8-int
+// header that echoes the click, so the host can tell which pixel the block belongs to.
+__global__ void __launch_bounds__(544) click_pmf_kernel(const float* __restrict__ dist, const int* __restrict__ click,
+                                                        int n_img, int H4, int W4, int* __restrict__ out_hdr,
+                                                        float* __restrict__ out_pmf) {
+  const int img = click[0], y4 = click[1], x4 = click[2];
+  const bool ok = img >= 0 && img < n_img && y4 >= 0 && y4 < H4 && x4 >= 0 && x4 < W4;
+  if (threadIdx.x < 8) out_hdr[threadIdx.x] = threadIdx.x == 7 ? (ok ? 1 : 0) : click[threadIdx.x];
+  if (!ok || threadIdx.x >= kBins) return;
+  const size_t HW4 = (size_t)H4 * W4;
+  out_pmf[threadIdx.x] = dist[((size_t)img * kBins + threadIdx.x) * HW4 + (size_t)y4 * W4 + x4];
+}
+
+cudaError_t launch_click_pmf(const float* dist, const int* click_dev, int n_img, int H4, int W4, int* out_hdr,
+                             float* out_pmf, cudaStream_t st) {
+  click_pmf_kernel<<<1, 544, 0, st>>>(dist, click_dev, n_img, H4, W4, out_hdr, out_pmf);
+  return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(1024) ab_reccs_kernel(const float* __restrict__ pmf, size_t bin_stride,
                                                         const float* __restrict__ pts, int K, int max_iter,
-                                                        double* __restrict__ out_all) {
+                                                        double* __restrict__ out_all, const int* __restrict__ dyn) {
   // CTA v = restart v: its first seed is the bin of weight-rank v (0 = heaviest); out_all[v] = [K][2]
   // centres, [K] mass, iterations, inertia
+  if (dyn) {                       // click graph: K comes from the click header written by click_pmf_kernel
+    K = dyn[3];
+    if (!dyn[7] || K < 1 || K > 32) return;
+  }
   double* out = out_all + (size_t)blockIdx.x * (3 * K + 2);
   __shared__ double w[kReccBins], mind[kReccBins];
   __shared__ double px[kReccBins], py[kReccBins];
@@ -790,8 +814,8 @@ __global__ void __launch_bounds__(1024) ab_reccs_kernel(const float* __restrict_
 }
 
 cudaError_t launch_ab_reccs(const float* pmf, size_t bin_stride, const float* pts_dev, int K, int max_iter,
-                            int n_init, double* out_dev, cudaStream_t st) {
-  ab_reccs_kernel<<<n_init, 1024, 0, st>>>(pmf, bin_stride, pts_dev, K, max_iter, out_dev);
+                            int n_init, double* out_dev, cudaStream_t st, const int* dyn) {
+  ab_reccs_kernel<<<n_init, 1024, 0, st>>>(pmf, bin_stride, pts_dev, K, max_iter, out_dev, dyn);
   return cudaGetLastError();
 }
 

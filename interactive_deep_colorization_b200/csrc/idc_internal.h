@@ -120,6 +120,7 @@ struct Options {
   int split_pairs = 1;    // cta_group::2 on the split-K (small batch) path
   int split_bn128 = 0;    // 128-column tiles on the split-K path (halves the partial-tile traffic of the reduction)
   int side_dist = 1;      // batch <= 4: run the dist head (class + softmax) on a side stream next to levels 9-10
+  int early_ab = 1;       // click graph: start the D2H of the ab map right after the last conv, next to the Lab->RGB kernel
   int tanh_scale = 110;   // regression head: tanh * 110 (model.py:175); the Caffe deploy nets use 100
 };
 
@@ -182,6 +183,10 @@ struct Ctx {
   // dist head off the critical path: class + softmax run on a side stream next to decoder levels 9-10
   cudaStream_t s_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t s_ab = nullptr;               // early D2H of the ab map (click graph)
+  cudaEvent_t ev_ab[2] = {nullptr, nullptr};
+  float* ab_early_dst = nullptr;             // set around run_forward by the small-batch host path
+  int image_n = 0;                           // idc_set_image: this many L planes are resident at the head of d_in
   cudaEvent_t ev_in[8] = {}, ev_out[8] = {};
   // CUDA graph cache for the batch-1 latency path
   cudaGraphExec_t graph_exec = nullptr;
@@ -195,6 +200,11 @@ struct Ctx {
   double* d_reccs = nullptr;    // idc_ab_reccs scratch (results of every restart, then the 529x2 gamut points)
   bool dist_resident = false;   // keep the dist of the last forward_host on the device (idc_fetch_dist)
   int dist_valid_n = 0;
+  // idc_set_click: the clicked pixel's pmf + K colour suggestions ride on a side branch of the click graph
+  bool click_mode = false;
+  int* h_click = nullptr; int* d_click = nullptr;   // {img, y4, x4, K, seq} in mapped host memory, read when the graph runs
+  char* d_clickout = nullptr; char* h_clickout = nullptr;   // [8-int header | 544 floats pmf | n_init x (3K+2) doubles]
+  bool click_served = false;    // h_clickout holds the answer for the click in its header
   // per-op profiling
   bool profiling = false;
   std::vector<std::vector<cudaEvent_t>> prof_runs;   // one event list per profiled forward
@@ -219,7 +229,9 @@ cudaError_t launch_lab2rgb(Ctx* c, int n, int h, int w, const float* L, float l_
 cudaError_t launch_decode313(Ctx* c, int n, float T, float* out_ab, cudaStream_t st);
 cudaError_t launch_dist313_pixel(Ctx* c, int img, int y, int x, float S, float* out313_dev, cudaStream_t st);
 cudaError_t launch_ab_reccs(const float* pmf, size_t bin_stride, const float* pts_dev, int K, int max_iter,
-                            int n_init, double* out_dev, cudaStream_t st);
+                            int n_init, double* out_dev, cudaStream_t st, const int* dyn = nullptr);
+cudaError_t launch_click_pmf(const float* dist, const int* click_dev, int n_img, int H4, int W4, int* out_hdr,
+                             float* out_pmf, cudaStream_t st);
 cudaError_t launch_global_stats(int h, int w, const uint8_t* rgb, const float* pts, float* out316, cudaStream_t st);
 cudaError_t launch_rgb2lab(int n, int h, int w, const uint8_t* rgb, double* lab, cudaStream_t st);
 cudaError_t launch_zoom_lab2rgb(const double* ab, int hin, int win, const double* Lfull, int H, int W, uint8_t* rgb,

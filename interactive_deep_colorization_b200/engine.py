@@ -50,6 +50,8 @@ class LhnContext(object):
         self.h = h
         self.ready = False
         self._pinned = []
+        # bookkeeping of the reference-facing wrappers that share this context (colorize_image.py: _click)
+        self._wrapper_click, self._wrapper_staged_l, self._wrapper_last, self._wrapper_shared = None, [], None, False
         for k, v in (options or {}).items():
             self.set_option(k, v)
 
@@ -112,14 +114,25 @@ class LhnContext(object):
         _lib.check(self.h, rc)
         return {"ab": out_ab, "dist": out_dist if want_dist else None, "rgb": out_rgb if want_rgb else None}
 
+    def set_image(self, L_mc):
+        """Upload the mean-centred L planes [n,1,H,W] once (the reference's set_image / load_image half of a session);
+        forward_host(None, ab, mask, ...) then reuses them.  None forgets the image."""
+        if L_mc is None:
+            _lib.check(self.h, self.lib.idc_set_image(self.h, 0, self.H, self.W, None))
+            return
+        assert L_mc.dtype == np.float32 and L_mc.flags["C_CONTIGUOUS"]
+        _lib.check(self.h, self.lib.idc_set_image(self.h, int(L_mc.shape[0]), self.H, self.W, _np_ptr(L_mc)))
+
     def forward_host(self, L_mc, ab, mask, maskcent=0.0, glob=None, want_dist=False, want_rgb=False,
                      out_ab=None, out_dist=None, out_rgb=None, want_abq=False, out_abq=None):
         """numpy float32 C-contiguous host arrays (pinned or pageable) -> dict of numpy arrays.
         Synchronous; includes H2D + D2H.  want_abq: also the reference's quantised output_ab
-        (rgb2lab(rgb)[1:], float64; implies want_rgb)."""
+        (rgb2lab(rgb)[1:], float64; implies want_rgb).  L_mc None = the image uploaded by set_image."""
         want_rgb = want_rgb or want_abq
-        n = L_mc.shape[0]
-        for a in (L_mc, ab, mask):
+        n = ab.shape[0]
+        if L_mc is not None:                 # an explicit L replaces the resident image: wrappers must re-stage theirs
+            self._wrapper_staged_l, self._wrapper_last = [], None
+        for a in (ab, mask) + (() if L_mc is None else (L_mc,)):
             assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
         if out_ab is None:
             out_ab = np.empty((n, 2, self.H, self.W), np.float32)
@@ -129,7 +142,7 @@ class LhnContext(object):
             out_rgb = np.empty((n, self.H, self.W, 3), np.uint8)
         if want_abq and out_abq is None:
             out_abq = np.empty((n, 2, self.H, self.W), np.float64)
-        rc = self.lib.idc_forward_host_q(self.h, n, self.H, self.W, _np_ptr(L_mc), _np_ptr(ab), _np_ptr(mask),
+        rc = self.lib.idc_forward_host_q(self.h, n, self.H, self.W, None if L_mc is None else _np_ptr(L_mc), _np_ptr(ab), _np_ptr(mask),
                                          float(maskcent), _np_ptr(glob) if glob is not None else None,
                                          _np_ptr(out_ab), _np_ptr(out_dist) if want_dist else None,
                                          _np_ptr(out_rgb) if want_rgb else None,
@@ -167,6 +180,12 @@ class LhnContext(object):
     def set_dist_resident(self, on=True):
         """Interactive mode: the dist head runs on every forward_host but stays on the device."""
         _lib.check(self.h, self.lib.idc_set_dist_resident(self.h, 1 if on else 0))
+
+    def set_click(self, img=0, y4=-1, x4=0, K=0):
+        """Announce the clicked pixel of the (H/4 x W/4) grid before forward_host: its pmf and K colour suggestions
+        come back with the same graph launch (fetch_dist / ab_reccs for that pixel are then host-side reads).
+        y4 < 0 switches the mode off."""
+        _lib.check(self.h, self.lib.idc_set_click(self.h, int(img), int(y4), int(x4), int(K)))
 
     def fetch_dist(self, img=0, y4=None, x4=None):
         """dist[img, :, y4, x4] (529 floats), or the whole [529, H/4, W/4] plane when y4 is None."""

@@ -43,6 +43,8 @@ def parse_args(argv=None):
     p.add_argument('--reference_root', type=str, default='.', help='checkout of the reference repo (for its ui/ package)')
     p.add_argument('--no_click_suggestions', action='store_true', help='keep the reference behaviour: suggestions only on load / reset')
     p.add_argument('--host_display', action='store_true', help='keep the numpy display step of compute_result')
+    p.add_argument('--separate_models', action='store_true',
+                   help='b200: two contexts (two forwards per click) like the reference, instead of one shared trunk')
     return p.parse_args(argv)
 
 
@@ -50,10 +52,16 @@ def build_models(args):
     """ideepcolor.py:60-74 for the B200 backends -> (colorModel, distModel)."""
     from . import colorize_image as CI
     if args.backend == 'b200':
+        # "PyTorch (same model used for both)" (ideepcolor.py:34-38): one checkpoint, so one trunk -- the distribution
+        # model shares the colour model's context and a click is ONE forward (ColorizeImageB200Dist.share_trunk)
+        share = not getattr(args, 'separate_models', False)
         colorModel = CI.ColorizeImageB200(Xd=args.load_size, maskcent=args.pytorch_maskcent)
-        colorModel.prep_net(gpu_id=args.gpu, path=args.color_model)
+        colorModel.prep_net(gpu_id=args.gpu, path=args.color_model, dist=share)
         distModel = CI.ColorizeImageB200Dist(Xd=args.load_size, maskcent=args.pytorch_maskcent)
-        distModel.prep_net(gpu_id=args.gpu, path=args.color_model, dist=True)
+        if share:
+            distModel.share_trunk(colorModel)
+        else:
+            distModel.prep_net(gpu_id=args.gpu, path=args.color_model, dist=True)
     elif args.backend == 'b200-caffe':
         colorModel = CI.ColorizeImageB200Caffe(Xd=args.load_size)
         colorModel.prep_net(args.gpu, caffemodel_path=args.color_caffemodel)

@@ -71,6 +71,33 @@ def run(tag, options, X=256):
           % (tag, pct(t_fwd, 50), min(t_fwd), pct(t_graph, 50), min(t_graph), pct(t_fetch, 50)))
     print("[%s] click: total p50 %.3f ms; SM clock after each click: median %d MHz (min %d, max %d)"
           % (tag, pct(np.add(t_fwd, t_fetch), 50), int(np.median(clocks)), min(clocks), max(clocks)))
+    # the shipped click: resident image (idc_set_image), announced click (idc_set_click, K = 9 suggestions on the side branch)
+    ctx.set_image(buf["L_mc"])
+    t_all, t_graph2 = [], []
+    for i in range(45):
+        loc = rs.randint(8, X - 8, 2)
+        CI.put_point(buf["ab"][0], buf["mask"][0], loc, 3, rs.uniform(-80, 80, 2))
+        y4, x4 = int(loc[0]) // 4, int(loc[1]) // 4
+        t0 = time.perf_counter()
+        ctx.set_click(0, y4, x4, 9)
+        ctx.forward_host(None, buf["ab"], buf["mask"], 0.5, want_rgb=True, out_ab=buf["out_ab"], out_rgb=buf["out_rgb"])
+        ctx.fetch_dist(0, y4, x4)
+        ctx.ab_reccs(0, y4, x4, K=9)
+        t_all.append((time.perf_counter() - t0) * 1e3)
+        lib.idc_debug_graph_timing(ctx.h, 1, ctypes.byref(ms))
+        t_graph2.append(ms.value)
+    print("[%s] announced click, resident image (forward + pmf + 9 suggestions): wall p50 %.3f ms (min %.3f), graph span p50 %.3f ms"
+          % (tag, pct(t_all[5:], 50), min(t_all[5:]), pct(t_graph2[5:], 50)))
+    ctx.set_click(0, -1, 0, 0)
+    t_all = []
+    for i in range(30):
+        t0 = time.perf_counter()
+        ctx.forward_host(None, buf["ab"], buf["mask"], 0.5, want_rgb=True, out_ab=buf["out_ab"], out_rgb=buf["out_rgb"])
+        t_all.append((time.perf_counter() - t0) * 1e3)
+        lib.idc_debug_graph_timing(ctx.h, 1, ctypes.byref(ms))
+        t_graph2.append(ms.value)
+    print("[%s] resident image, click mode off: forward_host wall p50 %.3f ms, graph span p50 %.3f ms"
+          % (tag, pct(t_all[5:], 50), pct(t_graph2[-20:], 50)))
     # spaced clicks: one per 50 ms, as a user would issue them (does the clock drop between clicks?)
     t_sp, c_sp = [], []
     for i in range(12):

@@ -43,6 +43,8 @@ def run(tag, options, per_op=True):
         torch.cuda.synchronize()
         print("[%s] stream-launched forward (dist+rgb): %.1f us each" % (tag, e0.elapsed_time(e1) * 1e3 / 50))
         ctx.close()
+    if os.environ.get("IDC_PER_OP_ONLY"):
+        return
     for want_dist in (True, False):
         for pinned in (False, True):
             ctx = util.make_ctx(sd, 256, 256, max_n=1, dist=True, use_graph=True, options=options)
