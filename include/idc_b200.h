@@ -81,7 +81,6 @@ int idc_create(int device, int max_n, int h, int w, unsigned flags, idc_ctx** ou
  *   "split_pairs"   0 / 1       run the split-K (small batch) launches as CTA pairs
  *   "direct_stores" 0 / 1       per-lane 16-byte stores instead of the warp-transposed ones
  *   "host_pipe"     0 / 1       idc_forward_host: chunked copy/compute overlap for batches >= 8
- *   "early_ab"      0 / 1       click graph: D2H of the ab map forks off right after the last conv (next to Lab->RGB)
  *   "pdl"           0 / 1       programmatic dependent launch between the kernels of one forward
  *   "side_dist"     0 / 1       batches <= 4: run the dist head (class + softmax) on a side stream / graph branch
  *   "tanh_scale"    110 / 100   regression head scale: tanh * 110 (model.py:175) or the Caffe nets' 100

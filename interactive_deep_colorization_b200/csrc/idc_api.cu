@@ -509,6 +509,15 @@ cudaError_t click_tail(Ctx* c, int n, const float* dist, cudaStream_t st) {
   return cudaMemcpyAsync(c->h_clickout, c->d_clickout, kClickCopy, cudaMemcpyDeviceToHost, st);
 }
 
+// persistent-grid cap (CTAs, even) that leaves kClickInit SMs to the side branch
+int side_branch_cap(Ctx* c) {
+  cudaDeviceProp prop;
+  static int sms[64] = {};
+  int& n = sms[c->dev < 64 ? c->dev : 0];
+  if (!n) { cudaGetDeviceProperties(&prop, c->dev); n = prop.multiProcessorCount; }
+  return ((n - kClickInit) / 2) * 2;
+}
+
 int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mask, float maskcent, const float* glob,
                 float* out_ab, float* out_dist, uint8_t* out_rgb, cudaStream_t st, const HostPipe* hp = nullptr,
                 double* out_abq = nullptr) {
@@ -548,7 +557,7 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
   // 9-10 do not depend on it -> it runs on a side stream (a parallel branch of the click graph) on the ~20 SMs the
   // 128-CTA launches of the main chain leave idle, instead of sitting between c8_3 and up9 on the critical path.
   const bool side_dist = c->opt.side_dist && !c->simt && out_dist && n <= 4 && !hp && !ev;
-  bool forked = false, ab_forked = false;
+  bool forked = false;
   for (auto& op : c->ops) {
     if (side_dist && op.kind == OP_CLASS && op.name == "class") {
       if (!c->s_side) {
@@ -585,23 +594,11 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
                                     (size_t)nk * 2 * HW * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
       }
     } else {
-      CUDA_TRY(c, umma_run_op(c, op, n, op.fuse_out_head ? out_ab : nullptr, (float)c->opt.tanh_scale, st));
-      if (op.fuse_out_head && c->ab_early_dst) {
-        // click graph: the D2H of the ab map starts as soon as the last conv is done, next to the Lab->RGB kernel
-        if (!c->s_ab) {
-          CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_ab, cudaStreamNonBlocking));
-          CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_ab[0], cudaEventDisableTiming));
-          CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_ab[1], cudaEventDisableTiming));
-        }
-        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        CUDA_TRY(c, cudaStreamIsCapturing(st, &cap));
-        CUDA_TRY(c, cudaEventRecord(c->ev_ab[0], st));
-        CUDA_TRY(c, cudaStreamWaitEvent(c->s_ab, c->ev_ab[0], 0));
-        CUDA_TRY(c, cudaMemcpyAsync(c->ab_early_dst, out_ab, (size_t)n * 2 * HW * sizeof(float), cudaMemcpyDeviceToHost, c->s_ab));
-        CUDA_TRY(c, cudaEventRecord(c->ev_ab[1], c->s_ab));
-        if (cap != cudaStreamCaptureStatusActive) pdl_break(c);   // live stream: the record sits between the two kernels
-        ab_forked = true;
-      }
+      // announced click: the suggestion kernel (8 CTAs of 1024 threads, a whole SM each) runs on the side branch next
+      // to decoder levels 9-10; a 148-CTA launch would queue behind it on 8 SMs and finish that much later.  Leaving 8
+      // SMs free costs nothing: 512 tiles are 4 rounds on 148 and on 140 CTAs alike.
+      const int cap = (forked && c->click_mode && c->d_clickout) ? side_branch_cap(c) : 0;
+      CUDA_TRY(c, umma_run_op(c, op, n, op.fuse_out_head ? out_ab : nullptr, (float)c->opt.tanh_scale, st, 0, cap));
     }
     mark();
   }
@@ -618,10 +615,6 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
   }
   if (forked) {
     CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_join, 0));   // join: whatever follows on `st` sees the distribution
-    pdl_break(c);
-  }
-  if (ab_forked) {
-    CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_ab[1], 0));
     pdl_break(c);
   }
   mark();
@@ -683,11 +676,11 @@ int idc_set_option(idc_ctx* c, const char* name, int value) {
       {"halo", &c->opt.halo}, {"pairs", &c->opt.pairs}, {"mt", &c->opt.mt}, {"chunk_kb", &c->opt.chunk_kb},
       {"split_k", &c->opt.split_k}, {"direct_stores", &c->opt.direct_stores}, {"host_pipe", &c->opt.host_pipe},
       {"pdl", &c->opt.pdl}, {"split_pairs", &c->opt.split_pairs}, {"tanh_scale", &c->opt.tanh_scale},
-      {"side_dist", &c->opt.side_dist}, {"split_bn128", &c->opt.split_bn128}, {"early_ab", &c->opt.early_ab}};
+      {"side_dist", &c->opt.side_dist}, {"split_bn128", &c->opt.split_bn128}};
   for (auto& t : tab)
     if (!strcmp(t.n, name)) {
       *t.v = value;
-      if (c->weights_ready && strcmp(name, "host_pipe") && strcmp(name, "tanh_scale") && strcmp(name, "side_dist") && strcmp(name, "early_ab")) {      // plan-time option changed after planning: re-plan
+      if (c->weights_ready && strcmp(name, "host_pipe") && strcmp(name, "tanh_scale") && strcmp(name, "side_dist")) {      // plan-time option changed after planning: re-plan
         CUDA_TRY(c, cudaSetDevice(c->dev));
         CUDA_TRY(c, cudaDeviceSynchronize());
         int rc = plan_engines(c);
@@ -863,28 +856,23 @@ static int forward_host_small(idc_ctx* c, int n, const float* L, const float* ab
       cp(c->d_in + off, c->h_in + off, in_floats * sizeof(float), cudaMemcpyHostToDevice);
     }
     int rc = IDC_OK;
-    // with an RGB post-process behind it, the D2H of the ab map forks off right after the last conv
-    const bool early_ab = want_rgb && c->opt.early_ab;
-    c->ab_early_dst = early_ab ? (direct ? out_ab : reinterpret_cast<float*>(hsm)) : nullptr;
     if (ce == cudaSuccess)
       rc = run_forward(c, n, dL, dab, dmask, maskcent, want_glob ? dglob : nullptr, dout, want_dist ? ddist : nullptr,
                        want_rgb ? drgb : nullptr, st, nullptr, want_q ? dq : nullptr);
-    c->ab_early_dst = nullptr;
     if (rc == IDC_OK) {
       if (direct) {
         const char* o0 = reinterpret_cast<const char*>(out_ab);
         const bool contig = (!want_rgb || reinterpret_cast<const char*>(out_rgb) == o0 + b_ab) &&
                             (!want_q || reinterpret_cast<const char*>(out_abq) == o0 + b_ab + b_rgb);
         if (contig) {
-          cp(reinterpret_cast<char*>(out_ab) + (early_ab ? b_ab : 0), dsm + (early_ab ? b_ab : 0),
-             out_bytes - (early_ab ? b_ab : 0), cudaMemcpyDeviceToHost);
+          cp(out_ab, dsm, out_bytes, cudaMemcpyDeviceToHost);
         } else {
-          if (!early_ab) cp(out_ab, dout, b_ab, cudaMemcpyDeviceToHost);
+          cp(out_ab, dout, b_ab, cudaMemcpyDeviceToHost);
           if (want_rgb) cp(out_rgb, drgb, b_rgb, cudaMemcpyDeviceToHost);
           if (want_q) cp(out_abq, dq, b_q, cudaMemcpyDeviceToHost);
         }
       } else {
-        cp(hsm + (early_ab ? b_ab : 0), dsm + (early_ab ? b_ab : 0), out_bytes - (early_ab ? b_ab : 0), cudaMemcpyDeviceToHost);
+        cp(hsm, dsm, out_bytes, cudaMemcpyDeviceToHost);
         if (copy_dist)
           cp(c->h_out + (size_t)c->max_n * 2 * HW, ddist, (size_t)n * 529 * HW4 * sizeof(float), cudaMemcpyDeviceToHost);
       }
@@ -1447,7 +1435,6 @@ int idc_destroy(idc_ctx* c) {
   if (c->h_clickout) cudaFreeHost(c->h_clickout);
   if (c->dbg_ev[0]) { cudaEventDestroy(c->dbg_ev[0]); cudaEventDestroy(c->dbg_ev[1]); }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
-  if (c->s_ab) { cudaStreamDestroy(c->s_ab); cudaEventDestroy(c->ev_ab[0]); cudaEventDestroy(c->ev_ab[1]); }
   if (c->s_side) { cudaStreamDestroy(c->s_side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
   if (c->s_in) {
     cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);

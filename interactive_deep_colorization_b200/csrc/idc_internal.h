@@ -118,9 +118,8 @@ struct Options {
   int host_pipe = 1;      // idc_forward_host: chunked copy/compute overlap for batches >= 8
   int pdl = 1;            // programmatic dependent launch between the kernels of a forward
   int split_pairs = 1;    // cta_group::2 on the split-K (small batch) path
-  int split_bn128 = 0;    // 128-column tiles on the split-K path (halves the partial-tile traffic of the reduction)
+  int split_bn128 = 1;    // 128-column tiles on the split-K path (halves the partial-tile traffic of the reduction)
   int side_dist = 1;      // batch <= 4: run the dist head (class + softmax) on a side stream next to levels 9-10
-  int early_ab = 1;       // click graph: start the D2H of the ab map right after the last conv, next to the Lab->RGB kernel
   int tanh_scale = 110;   // regression head: tanh * 110 (model.py:175); the Caffe deploy nets use 100
 };
 
@@ -183,9 +182,6 @@ struct Ctx {
   // dist head off the critical path: class + softmax run on a side stream next to decoder levels 9-10
   cudaStream_t s_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  cudaStream_t s_ab = nullptr;               // early D2H of the ab map (click graph)
-  cudaEvent_t ev_ab[2] = {nullptr, nullptr};
-  float* ab_early_dst = nullptr;             // set around run_forward by the small-batch host path
   int image_n = 0;                           // idc_set_image: this many L planes are resident at the head of d_in
   cudaEvent_t ev_in[8] = {}, ev_out[8] = {};
   // CUDA graph cache for the batch-1 latency path

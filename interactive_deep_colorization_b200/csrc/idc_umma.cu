@@ -1260,7 +1260,9 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
     // Draining a chunk costs ~8 serial TMEM round trips (~1600 cycles for 128 columns per thread), about
     // one k-block of MMA time at 256 output columns per CTA tile; the Cout<=128 layers have short K
     // (few chunks per tile to amortise the tile epilogue), so they use 2 -> 2.1e-4 end to end.
-    int g = c->fast ? 4 : (op.bn_tile <= 128 ? 2 : 1);
+    // (the rule follows the layer's width, not the tile's: the 128-column tiles of the split-K path keep chunk 1)
+    const int natural = (op.cout_pad % 256 == 0) ? 256 : (op.cout_pad % 192 == 0) ? 192 : (op.cout_pad % 128 == 0) ? 128 : 64;
+    int g = c->fast ? 4 : (natural <= 128 ? 2 : 1);
     if (c->opt.chunk_kb >= 1) g = c->opt.chunk_kb;
     q.chunk_kb = g;
   }
@@ -1308,7 +1310,7 @@ cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float ou
   UmmaPlan* pl = static_cast<UmmaPlan*>(op.umma_plan);
   if (!pl) return cudaErrorInvalidValue;
   UmmaParams prm = pl->prm;
-  prm.max_ctas = (max_ctas > 0 && pl->split_k == 1 && pl->cg == 1) ? max_ctas : 0;
+  prm.max_ctas = (max_ctas > 0 && pl->split_k == 1) ? (max_ctas / pl->cg) * pl->cg : 0;   // split-K needs all items co-resident
   prm.img0 = img0;
   prm.n_img = img0 + n;
   if (img0 && pl->split_k > 1) return cudaErrorInvalidValue;   // image chunks are a large-batch feature

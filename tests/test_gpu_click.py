@@ -1,8 +1,7 @@
 """GPU: the click itself (BASELINE config 5) -- the pieces that ride on the click graph besides the conv trunk:
 the resident image (idc_set_image: L uploaded once per photo), the announced click (idc_set_click: the clicked pixel's
-pmf and K colour suggestions on the dist head's side branch, returned with the same graph launch), the early D2H of the
-ab map, and the shared trunk of the colour / distribution wrapper pair.  Everything must be bit-identical to the plain
-calls it short-cuts."""
+pmf and K colour suggestions on the dist head's side branch, returned with the same graph launch) and the shared trunk
+of the colour / distribution wrapper pair.  Everything must be bit-identical to the plain calls it short-cuts."""
 import numpy as np
 import pytest
 
@@ -102,27 +101,6 @@ def test_announced_click_returns_pmf_and_suggestions_with_the_forward(synth_sd):
     assert np.array_equal(r["ab"], p["ab"])
     assert np.array_equal(ctx.fetch_dist(0, y4, x4), want_pmf)
     ctx.close(); plain.close()
-
-
-def test_early_ab_copy_option_is_bit_identical(synth_sd):
-    X = 64
-    L, ab, m = synth.synthetic_batch(2, X, seed=11, max_hints=4)
-    outs = []
-    for early in (1, 0):
-        ctx = util.make_ctx(synth_sd, X, X, max_n=2, dist=True, options={"early_ab": early})
-        for pinned in (False, True):
-            if pinned:
-                buf = ctx.click_buffers(2)
-                buf["L_mc"][...] = L; buf["ab"][...] = ab; buf["mask"][...] = m
-                r = ctx.forward_host(buf["L_mc"], buf["ab"], buf["mask"], 0.5, want_rgb=True, want_abq=True,
-                                     out_ab=buf["out_ab"], out_rgb=buf["out_rgb"], out_abq=buf["out_abq"])
-            else:
-                r = ctx.forward_host(L, ab, m, 0.5, want_rgb=True, want_abq=True)
-            outs.append({k: np.array(r[k]) for k in ("ab", "rgb", "abq")})
-        ctx.close()
-    for o in outs[1:]:
-        for k in ("ab", "rgb", "abq"):
-            assert np.array_equal(outs[0][k], o[k]), k
 
 
 def test_shared_trunk_pair_is_one_forward_per_click(synth_sd):

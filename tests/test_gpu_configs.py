@@ -148,7 +148,7 @@ def test_plan_options_agree(synth_sd):
     ref = g["mc1_rand5_ab_raw"]
     outs = {}
     for name, opts in (("default", {}), ("no_pdl", {"pdl": 0}), ("no_side_dist", {"side_dist": 0}),
-                       ("no_split_pairs", {"split_pairs": 0}), ("split_bn128", {"split_bn128": 1}),
+                       ("no_split_pairs", {"split_pairs": 0}), ("split_bn256", {"split_bn128": 0}),
                        ("no_halo", {"halo": 0}), ("halo_all", {"halo": 3})):
         ctx = util.make_ctx(synth_sd, 256, 256, max_n=1, dist=True, options=opts)
         r = ctx.forward_host(L1, a1, m1, 0.5, want_dist=True, want_rgb=True)
@@ -163,7 +163,7 @@ def test_plan_options_agree(synth_sd):
         assert np.array_equal(outs["default"]["ab"], outs[k]["ab"]), k
         assert np.array_equal(outs["default"]["dist"], outs[k]["dist"]), k
         assert np.array_equal(outs["default"]["rgb"], outs[k]["rgb"]), k
-    for k in ("no_split_pairs", "split_bn128", "no_halo", "halo_all"):
+    for k in ("no_split_pairs", "split_bn256", "no_halo", "halo_all"):
         assert util.maxabs(outs[k]["ab"], outs["default"]["ab"]) < 3e-4, k
     # batch 4 on a max_n = 4 context (halo + pairs plans differ from the batch-1 context)
     L, ab, m = synth.synthetic_batch(4, 256, seed=77, max_hints=6)
