@@ -676,7 +676,7 @@ int idc_set_option(idc_ctx* c, const char* name, int value) {
       {"halo", &c->opt.halo}, {"pairs", &c->opt.pairs}, {"mt", &c->opt.mt}, {"chunk_kb", &c->opt.chunk_kb},
       {"split_k", &c->opt.split_k}, {"direct_stores", &c->opt.direct_stores}, {"host_pipe", &c->opt.host_pipe},
       {"pdl", &c->opt.pdl}, {"split_pairs", &c->opt.split_pairs}, {"tanh_scale", &c->opt.tanh_scale},
-      {"side_dist", &c->opt.side_dist}, {"split_bn128", &c->opt.split_bn128}};
+      {"side_dist", &c->opt.side_dist}, {"split_bn128", &c->opt.split_bn128}, {"halo_split", &c->opt.halo_split}};
   for (auto& t : tab)
     if (!strcmp(t.n, name)) {
       *t.v = value;

@@ -1074,6 +1074,7 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
     const int t = ceil_div(op.Wl, wb) * ceil_div(op.Hl, hb);
     if (t < best) { best = t; op.wbox = wb; op.hbox = hb; }
   }
+  bool halo_shape = false;
   // HALO: stride-1 3x3 convs of one source with 128 output columns per tile (c2_2, c9_2, c10_2: the layers that are
   // shared-memory-bandwidth bound with per-tap boxes) load one 18x10-pixel halo tile per 64 input channels instead of
   // one box per tap, when the launch fills the machine.  Measured at 64 x 256^2: c2_2 0.76 -> 0.63 ms, c9_2 0.76 ->
@@ -1082,7 +1083,7 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   // (also 64 columns, also tiny launches) for the unit tests.
   {
     const int mode = c->opt.halo;
-    bool ok = mode >= 1 && !c->fast && op.ncls == 1 && op.ntaps == 9 && (op.bn_tile == 128 || (mode >= 3 && op.bn_tile == 64));
+    bool ok = mode >= 1 && !c->fast && op.ncls == 1 && op.ntaps == 9;
     unsigned seen = 0;
     for (int t = 0; ok && t < op.ntaps; ++t) {
       const Tap& tp = op.taps[0][t];
@@ -1090,7 +1091,9 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
       else seen |= 1u << ((tp.ty + 1) * 3 + tp.tx + 1);
     }
     if (ok && (seen != 0x1FFu || op.src[op.taps[0][0].src].cin % kBK)) ok = false;
-    if (ok) {   // only launches that fill the machine (no split-K on this path)
+    halo_shape = ok;                     // a stride-1 3x3 conv of one source: the split-K path may still pick halo tiles
+    if (ok && !(op.bn_tile == 128 || (mode >= 3 && op.bn_tile == 64))) ok = false;
+    if (ok) {   // only launches that fill the machine (the split-K path decides for itself below)
       const long T = (long)c->max_n * ceil_div(op.Hl, 16) * ceil_div(op.Wl, 8) * (op.cout_pad / op.bn_tile);
       if (T < 2L * pl->num_sms && mode < 3) ok = false;
     }
@@ -1158,6 +1161,14 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
         if (S3 > 4) S3 = 4;                                // 128 columns = 4 pieces of 32
         if (c->opt.split_k >= 1 && c->opt.split_k <= S3) S3 = c->opt.split_k;
         if (S3 >= 2) { op.bn_tile = 128; S = S3; Tw = T3 * 2; }
+        // ... and with 128 columns the stride-1 3x3 layers can take the halo-tile A operand: a K slice of whole input
+        // groups (9 taps each) loads ONE 18x10-pixel halo per group instead of 9 boxes of 128 pixels, which cuts the
+        // L2 -> SM operand traffic of a slice from 48 to ~21 KB per k-block (option halo_split).
+        if (S3 >= 2 && c->opt.halo_split && halo_shape && nkb % 9 == 0 && (nkb / 9) % S3 == 0 &&
+            ceil_div(op.Hl, 16) * ceil_div(op.Wl, 8) == ty * tx) {
+          pl->halo = true;
+          op.wbox = 8; op.hbox = 16;
+        }
       }
     }
     pl->split_k = S;

@@ -109,3 +109,96 @@ def test_launcher_argument_surface_and_click_hook():
     import pytest
     with pytest.raises(SystemExit):
         launcher.build_models(launcher.parse_args(["--backend", "nope"]))
+
+
+class _FakeCtx(object):
+    """Stands in for LhnContext in the wrapper-logic tests: 'forward' is a cheap deterministic function of the staged
+    image and hints, so the tests can tell a re-used result from a recomputed one without a GPU."""
+
+    def __init__(self, X):
+        self.H = self.W = X
+        self.device = 0
+        self._wrapper_click, self._wrapper_staged_l, self._wrapper_last, self._wrapper_shared = None, [], None, False
+        self.calls, self.image_uploads, self.L = 0, 0, None
+
+    def click_buffers(self, n=1, glob=False):
+        X = self.H
+        return {"L_mc": np.zeros((n, 1, X, X), np.float32), "ab": np.zeros((n, 2, X, X), np.float32),
+                "mask": np.zeros((n, 1, X, X), np.float32), "glob": np.zeros((n, 316), np.float32) if glob else None,
+                "out_ab": np.zeros((n, 2, X, X), np.float32), "out_rgb": np.zeros((n, X, X, 3), np.uint8),
+                "out_abq": np.zeros((n, 2, X, X), np.float64)}
+
+    def set_image(self, L):
+        self.L = None if L is None else np.array(L)
+        self.image_uploads += 1
+
+    def set_dist_resident(self, on=True):
+        pass
+
+    def set_click(self, *a):
+        self.click = a
+
+    def forward_host(self, L_mc, ab, mask, maskcent=0.0, glob=None, want_rgb=False, want_abq=False, out_ab=None,
+                     out_rgb=None, out_abq=None, **kw):
+        assert L_mc is None and self.L is not None        # the wrappers use the resident image
+        self.calls += 1
+        out_ab[...] = 0.25 * ab + 0.5 * mask + 0.01 * self.L + maskcent
+        if out_rgb is not None:
+            out_rgb[...] = (np.abs(out_ab[:, :1]).transpose(0, 2, 3, 1) * 50).astype(np.uint8)
+        if out_abq is not None:
+            out_abq[...] = np.round(out_ab)
+        return {"ab": out_ab, "rgb": out_rgb, "abq": out_abq, "dist": None}
+
+    def fetch_dist(self, img, y4, x4):
+        return np.full(529, 1.0 / 529, np.float32)
+
+
+class _FakeNet(object):
+    dist, b200_device = True, 0
+
+    def __init__(self, X):
+        self.ctx = _FakeCtx(X)
+
+    def _context(self, H, W, n):
+        return self.ctx
+
+
+def test_shared_trunk_bookkeeping_without_a_gpu():
+    """ColorizeImageB200Dist.share_trunk: one forward per (image, hints) pair whichever model asks first; a changed
+    image, changed hints or a different maskcent on one side always recompute; the image is uploaded once per photo."""
+    X = 16
+    rs = np.random.RandomState(0)
+    cm = CI.ColorizeImageB200(Xd=X, maskcent=True, gpu_prepost=False)
+    cd = CI.ColorizeImageB200Dist(Xd=X, maskcent=True)
+    cd.gpu_prepost = False
+    cm.net, cm.net_set = _FakeNet(X), True
+    cd.share_trunk(cm)
+    ctx = cm.net.ctx
+    assert ctx._wrapper_shared and cd.net is cm.net
+    img = rs.randint(0, 256, (X, X, 3)).astype(np.uint8)
+    cm.set_image(img); cd.set_image(img.copy())
+    ab, m = np.zeros((2, X, X)), np.zeros((1, X, X))
+    CI.put_point(ab, m, [5, 6], 1, [30, -20])
+    rgb = cm.net_forward(ab, m)
+    assert ctx.calls == 1 and ctx.image_uploads == 1
+    ret = cd.net_forward(ab.copy(), m.copy())                      # same image (another array object), same hints
+    assert ctx.calls == 1 and np.array_equal(ret, cm.output_ab_raw * 110.0) and cd.dist_ab_set
+    CI.put_point(ab, m, [9, 3], 1, [-10, 44])
+    ret2 = cd.net_forward(ab, m)                                   # new hints: the dist model pays ...
+    assert ctx.calls == 2 and not np.array_equal(ret2, ret)
+    rgb2 = cm.net_forward(ab.copy(), m.copy())                     # ... and the colour model rides along
+    assert ctx.calls == 2 and ctx.image_uploads == 1 and not np.array_equal(rgb2, rgb)
+    assert np.array_equal(cm.output_ab_raw * 110.0, ret2)
+    cm.net_forward(ab, m)                                          # asking again recomputes nothing either
+    assert ctx.calls == 2
+    cd.set_image(img[::-1].copy())                                 # another photo on one side only
+    ret3 = cd.net_forward(ab, m)
+    assert ctx.calls == 3 and ctx.image_uploads == 2 and not np.array_equal(ret3, ret2)
+    cm.net_forward(ab, m)                                          # the colour model still holds the first photo
+    assert ctx.calls == 4 and ctx.image_uploads == 3
+    cd.mask_cent = 0.0                                             # different centring -> different network input
+    cd.set_image(img.copy())
+    cd.net_forward(ab, m)
+    assert ctx.calls == 5
+    cd.hint_click(8, 4, K=9)
+    assert ctx.click == (0, 2, 1, 9)
