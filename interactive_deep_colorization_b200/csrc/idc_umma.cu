@@ -71,6 +71,7 @@ struct UmmaParams {
   int n_amaps;         // entries of `amaps` (prefetched in the prologue)
   int max_ctas;        // host side only: grid cap for side-branch launches
   int halo_groups;     // HALO kernels: 64-channel input groups (K = 9 taps x halo_groups k-blocks); kblk = {-, B k-column, dy+1, dx+1}
+  int prologue_sync2;  // pairs: extra cluster barrier between barrier init and TMEM allocation (option, default 0)
   int img0;            // first image of this launch (n_img = img0 + images of the launch): idc_forward_host
                        // runs the last op in image chunks so that the D2H of a chunk overlaps the next one
 };
@@ -114,6 +115,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 6000000000LL) mbar_timeout(err, code);
   }
+}
+
+// Chain launches: poll side of the grid-wide arrive counter (bounded like every other wait).
+__device__ __forceinline__ void grid_wait(const int* bar, int target, int* err) {
+  int seen;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+  if (seen >= target) return;
+  const long long t0 = clock64();
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+    if (seen < target && clock64() - t0 > 6000000000LL) mbar_timeout(err, 8);
+  } while (seen < target);
 }
 
 // one lane of a converged warp (warp-uniform control flow keeps descriptors / addresses in uniform
@@ -326,11 +339,16 @@ struct SmemPlan {
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <int BN, int MT, int CG, bool SPLIT, bool HALO = false>
-__global__ void __launch_bounds__(kThreads, 1)
-umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_constant__ CUtensorMap bmap_lo,
-                 const UmmaParams p) {
+// CHAIN: one launch runs `nl` consecutive layers that share a tile configuration (the split-K layers of the interactive
+// path, conv3_1 ... conv8_3): barriers, TMEM and the operand ring stay alive, layer l+1's first weight tiles stream in
+// while layer l is still being reduced, and a grid-wide arrive / poll counter (`gridbar`) replaces the launch boundary:
+// a CTA's producer loads layer l+1's activations only after EVERY CTA has stored its part of layer l.
+template <int BN, int MT, int CG, bool SPLIT, bool HALO, bool CHAIN>
+__device__ __forceinline__ void conv_body(const CUtensorMap* bhi_list, const CUtensorMap* blo_list,
+                                          const UmmaParams* plist, const int nl, int* gridbar) {
+  static_assert(!(HALO && CHAIN), "chained launches use per-tap boxes");
   using SP = SmemPlan<BN, MT, CG, SPLIT, HALO>;
+  const UmmaParams& p0 = plist[0];
   constexpr int STAGES = SP::kStages;
   constexpr bool PAIR = CG == 2;
   extern __shared__ uint8_t smem_raw[];
@@ -354,19 +372,19 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
   float* s_red = reinterpret_cast<float*>(s_bar + 32);   // [128][2] fused-head partial sums, after the 256-byte barrier block
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long t_kernel0 = (IDC_CTA_COUNTERS && p.dbgbuf) ? clock64() : 0;
+  const long long t_kernel0 = (IDC_CTA_COUNTERS && p0.dbgbuf) ? clock64() : 0;
 
   // ---- one-time setup ----
-  if (p.wout) {
-    for (int i = threadIdx.x; i < 256; i += kThreads) s_head[i] = p.wout[i];
-    if (threadIdx.x < 2) s_head[256 + threadIdx.x] = p.bout[threadIdx.x];
+  if (!CHAIN && p0.wout) {
+    for (int i = threadIdx.x; i < 256; i += kThreads) s_head[i] = p0.wout[i];
+    if (threadIdx.x < 2) s_head[256 + threadIdx.x] = p0.bout[threadIdx.x];
   }
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   if (threadIdx.x == 32) {                          // descriptors are input-independent: fetch them during the prologue
-    prefetch_tmap(&bmap_hi);
-    if (SPLIT) prefetch_tmap(&bmap_lo);
-    for (int i = 0; i < p.n_amaps; ++i) prefetch_tmap(p.amaps + i);
+    prefetch_tmap(bhi_list);
+    if (SPLIT) prefetch_tmap(blo_list);
+    for (int i = 0; i < p0.n_amaps; ++i) prefetch_tmap(p0.amaps + i);
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -384,7 +402,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (PAIR) cluster_sync_all();                      // peer barriers exist before anything can arrive on them
+  // One cluster barrier covers both "the peer's mbarriers exist" and "TMEM is allocated": nothing touches the peer
+  // before the barrier below (p.prologue_sync2 = 1 restores the extra barrier in front of the allocation).
+  if (PAIR && p0.prologue_sync2) cluster_sync_all();
   if (warp == 1) {
     if (PAIR) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
@@ -405,10 +425,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
   pdl_launch_dependents();                           // the next kernel of the forward may start its own prologue
   if (warp != 0) pdl_wait();                         // warp 0 first requests its weight tiles (see the producer)
 
-  const int tiles_per_img = p.tiles_y * p.tiles_x;
-  const int G = p.chunk_kb;
   long long t_wait_tfull_g = 0, t_drain_g = 0, t_epi_g = 0, t_splitk_g = 0, t_spin_g = 0;
-  const int S = p.split_k;
+  const int n_layers = CHAIN ? nl : 1;
 
   if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
   if (warp == 0) {
@@ -417,9 +435,21 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       uint32_t hcount = 0;                               // HALO: halo loads issued (slot = hcount & 1)
+      for (int l = 0; l < n_layers; ++l) {
+      const UmmaParams& p = plist[l];
+      const CUtensorMap& bmap_hi = bhi_list[l];
+      const CUtensorMap& bmap_lo = blo_list[l];
+      const int tiles_per_img = p.tiles_y * p.tiles_x;
+      const int S = p.split_k;
+      if (CHAIN && l + 1 < n_layers && elect_one()) {    // the next layer's descriptors: fetched a whole layer ahead
+        prefetch_tmap(bhi_list + l + 1);
+        if (SPLIT) prefetch_tmap(blo_list + l + 1);
+        for (int i = 0; i < plist[l + 1].n_amaps; ++i) prefetch_tmap(plist[l + 1].amaps + i);
+      }
       // Weights never depend on the previous layer: request the weight tiles of this CTA's first k-blocks BEFORE
-      // pdl_wait(), so they stream in while the predecessor kernel drains.  The stage's `full` barrier is armed
-      // with the byte count of the whole stage; the activation boxes follow after the wait.
+      // the dependency wait (pdl_wait / the chain's grid barrier), so they stream in while the predecessor drains.
+      // The stage's `full` barrier is armed with the byte count of the whole stage; the activation boxes follow
+      // after the wait.  (CHAIN: the ring position may still hold the previous layer's last k-blocks -> wait for it.)
       const int w0 = blockIdx.x / CG;
       int npre = 0;
       if (w0 < p.total_tiles * S) {
@@ -432,10 +462,13 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         const int brow = cls * p.cout_pad + nt * BN + (int)cta_rank * (BN / CG);
         const int4* kb = p.kblk + cls * p.nkb;
         npre = kend - kbeg < STAGES ? kend - kbeg : STAGES;
-        if (elect_one()) {
-          for (int i = 0; i < npre; ++i) {
-            const uint32_t fb = smem_u32(&full_bar[i]);
-            const uint32_t sb = smem_u32(smem + i * SP::kStageBytes) + (SPLIT ? 2 : 1) * SP::kAStage;
+        int st = stage;
+        uint32_t ph = phase;
+        for (int i = 0; i < npre; ++i) {
+          if (CHAIN) mbar_wait(smem_u32(&empty_bar[st]), ph ^ 1, p.err, 1);
+          if (elect_one()) {
+            const uint32_t fb = smem_u32(&full_bar[st]);
+            const uint32_t sb = smem_u32(smem + st * SP::kStageBytes) + (SPLIT ? 2 : 1) * SP::kAStage;
             const int kcol = HALO ? __ldg(kb + kbeg + i).y : (kbeg + i) * kBK;
             if (PAIR) {
               if (leader) mbar_expect_tx(fb, 2 * SP::kStageBytes); else mbar_arrive_rank0(fb);
@@ -447,10 +480,16 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
               if (SPLIT) tma_load_2d(sb + SP::kBBytes, &bmap_lo, fb, kcol, brow);
             }
           }
+          __syncwarp();
+          if (++st == STAGES) { st = 0; ph ^= 1; }
         }
-        __syncwarp();
       }
-      pdl_wait();                                        // activations of the previous layer are complete and visible
+      if (!CHAIN || l == 0) {
+        pdl_wait();                                      // activations of the previous layer are complete and visible
+      } else if (w0 < p.total_tiles * S) {
+        grid_wait(gridbar, l * (int)gridDim.x, p.err);   // every CTA has stored its part of layer l-1 ...
+        asm volatile("fence.proxy.async;" ::: "memory");  // ... and TMA (async proxy) may read it
+      }
       for (int w = w0; w < p.total_tiles * S; w += gridDim.x / CG) {
         const int tile = w / S, ks = w - tile * S;
         const int kbeg = (ks * p.nkb) / S, kend = ((ks + 1) * p.nkb) / S;
@@ -546,6 +585,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      }   // layers
     }
   } else if (warp == 1 && leader) {
     // =============================== MMA issuer (pairs: leader CTA only) ========
@@ -553,10 +593,14 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       constexpr uint32_t idesc = make_idesc(BN, kBM * CG);
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t cc = 0;                                   // chunk counter (persists across tiles)
+      uint32_t cc = 0;                                   // chunk counter (persists across tiles and layers)
       uint32_t hcount = 0;                               // HALO: halo tiles consumed
       long long t_wait_tempty = 0, t_wait_full = 0, t_first_full = 0;
       const long long t_start = clock64();
+      for (int l = 0; l < n_layers; ++l) {
+      const UmmaParams& p = plist[l];
+      const int G = p.chunk_kb;
+      const int S = p.split_k;
       for (int w = blockIdx.x / CG; w < p.total_tiles * S; w += gridDim.x / CG) {
         const int ks = w % S;
         const int kbeg = (ks * p.nkb) / S, kend = ((ks + 1) * p.nkb) / S;
@@ -642,7 +686,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
           }
         }
       }
-      if (IDC_CTA_COUNTERS && p.dbgbuf && lane == 0) {
+      }   // layers
+      if (IDC_CTA_COUNTERS && p0.dbgbuf && lane == 0) {
+        const UmmaParams& p = p0;
         p.dbgbuf[blockIdx.x * 16 + 0] = clock64() - t_start;
         p.dbgbuf[blockIdx.x * 16 + 1] = t_wait_tempty;
         p.dbgbuf[blockIdx.x * 16 + 2] = t_wait_full;
@@ -661,8 +707,15 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
     const int c_base = (MT == 2) ? 0 : half * CH;          // first output column of this thread
     const int t_base = (MT == 2) ? half * BN : half * CH;   // its first TMEM column inside a chunk buffer
     uint32_t cc = 0;
-    int staged_key = -1;
     long long t_epi = 0, t_wait_tfull = 0, t_drain = 0, t_splitk = 0, t_spin = 0;
+    for (int l = 0; l < n_layers; ++l) {
+    const UmmaParams& p = plist[l];
+    const int tiles_per_img = p.tiles_y * p.tiles_x;
+    const int G = p.chunk_kb;
+    const int S = p.split_k;
+    int staged_key = -1;
+    if (CHAIN && blockIdx.x / CG >= p.total_tiles * S && l > 0 && et == 0)
+      grid_wait(gridbar, l * (int)gridDim.x, p.err);   // idle in this layer: still arrive only after the previous barrier
     for (int w = blockIdx.x / CG; w < p.total_tiles * S; w += gridDim.x / CG) {
       const int tile = w / S, ks = w - tile * S;
       const int kbeg = (ks * p.nkb) / S, kend = ((ks + 1) * p.nkb) / S;
@@ -954,11 +1007,25 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
         }
       }
     }
+    if (CHAIN) {
+      // grid barrier, arrive side: this CTA's part of layer l is stored (and its split-K counters are released)
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et == 0) {
+        __threadfence();
+        const int old = atomicAdd(gridbar, 1);
+        if (l == n_layers - 1 && old == n_layers * (int)gridDim.x - 1) {   // last arrival of the launch: reset for the next one
+          *gridbar = 0;
+          __threadfence();
+        }
+      }
+    }
+    }   // layers
     t_wait_tfull_g = t_wait_tfull; t_drain_g = t_drain; t_epi_g = t_epi; t_splitk_g = t_splitk; t_spin_g = t_spin;
   }
 
   // ---- teardown ----
-  if (IDC_CTA_COUNTERS && p.dbgbuf && warp == 4 && lane == 0) {
+  if (IDC_CTA_COUNTERS && p0.dbgbuf && warp == 4 && lane == 0) {
+    const UmmaParams& p = p0;
     p.dbgbuf[blockIdx.x * 16 + 3] = t_wait_tfull_g;
     p.dbgbuf[blockIdx.x * 16 + 4] = t_drain_g;
     p.dbgbuf[blockIdx.x * 16 + 5] = t_epi_g;
@@ -977,6 +1044,26 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_const
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)SP::kTmemCols)
                    : "memory");
   }
+}
+
+template <int BN, int MT, int CG, bool SPLIT, bool HALO = false>
+__global__ void __launch_bounds__(kThreads, 1)
+umma_conv_kernel(const __grid_constant__ CUtensorMap bmap_hi, const __grid_constant__ CUtensorMap bmap_lo,
+                 const __grid_constant__ UmmaParams p) {
+  conv_body<BN, MT, CG, SPLIT, HALO, false>(&bmap_hi, &bmap_lo, &p, 1, nullptr);
+}
+
+// a run of consecutive layers in one launch (see conv_body); everything lives in the constant bank
+constexpr int kChainMax = 20;
+struct ChainParams {
+  CUtensorMap bhi[kChainMax], blo[kChainMax];
+  UmmaParams layer[kChainMax];
+  int nl;
+  int* gridbar;
+};
+template <int BN, int MT, int CG, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1) umma_chain_kernel(const __grid_constant__ ChainParams P) {
+  conv_body<BN, MT, CG, SPLIT, false, true>(P.bhi, P.blo, P.layer, P.nl, P.gridbar);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1297,6 +1384,7 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   q.store_mode = 1;
   if (c->opt.direct_stores) q.store_mode = 0;
   q.err = c->d_err;
+  q.prologue_sync2 = c->opt.prologue_sync2;
   q.img0 = 0;
   q.dbgbuf = nullptr;
   return IDC_OK;
@@ -1316,11 +1404,12 @@ bool umma_op_uses_split_k(const ConvOp& op) {
   return pl && pl->split_k > 1;
 }
 
-cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float out_mult, cudaStream_t st, int img0,
-                        int max_ctas) {
+// launch parameters of one op for `n` images (shared by the single-op and the chained launch)
+static cudaError_t umma_prepare(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float out_mult, int img0, int max_ctas,
+                                UmmaParams& prm) {
   UmmaPlan* pl = static_cast<UmmaPlan*>(op.umma_plan);
   if (!pl) return cudaErrorInvalidValue;
-  UmmaParams prm = pl->prm;
+  prm = pl->prm;
   prm.max_ctas = (max_ctas > 0 && pl->split_k == 1) ? (max_ctas / pl->cg) * pl->cg : 0;   // split-K needs all items co-resident
   prm.img0 = img0;
   prm.n_img = img0 + n;
@@ -1336,6 +1425,72 @@ cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float ou
   if (pl->split_k > 1 && (!prm.ws || !prm.counters)) return cudaErrorInvalidValue;
   prm.out_mult = out_mult;
   if (op.fuse_out_head && !out_ab_fused) return cudaErrorInvalidValue;
+  return cudaSuccess;
+}
+
+// Chain launches (conv_body<..., CHAIN>): consecutive ops that all run as 128-column split-K CTA pairs with per-tap
+// boxes and write an ordinary activation -- at 256^2 / batch 1 that is conv3_1 ... conv8_3, 18 of the 26 conv launches.
+bool umma_op_chainable(const Ctx* c, const ConvOp& op) {
+  const UmmaPlan* pl = static_cast<const UmmaPlan*>(op.umma_plan);
+  return pl && !c->fast && op.bn_tile == 128 && pl->mt == 1 && pl->cg == 2 && pl->split_k > 1 && !pl->halo &&
+         !op.fuse_out_head && !op.out_f32 && op.out_buf >= 0;
+}
+
+cudaError_t umma_run_chain(Ctx* c, int first, int last, int n, cudaStream_t st) {
+  const int nl = last - first + 1;
+  if (nl < 2 || nl > kChainMax || !c->chain_bar) return cudaErrorInvalidValue;
+  ChainParams P;                                         // 10 KB of kernel parameters, copied by the launch itself
+  int grid = 0, dev = 0;
+  for (int k = 0; k < nl; ++k) {
+    ConvOp& op = c->ops[first + k];
+    if (!umma_op_chainable(c, op)) return cudaErrorInvalidValue;
+    UmmaPlan* pl = static_cast<UmmaPlan*>(op.umma_plan);
+    cudaError_t e = umma_prepare(c, op, n, nullptr, (float)c->opt.tanh_scale, 0, 0, P.layer[k]);
+    if (e != cudaSuccess) return e;
+    P.layer[k].dbgbuf = nullptr;
+    P.bhi[k] = pl->bmap_hi; P.blo[k] = pl->bmap_lo;
+    const long items = (long)P.layer[k].total_tiles * P.layer[k].split_k;
+    if (items * 2 > pl->num_sms) return cudaErrorInvalidValue;       // every work item of every layer must be resident
+    if (items * 2 > grid) grid = (int)items * 2;
+    dev = pl->dev;
+  }
+  P.nl = nl;
+  P.gridbar = c->chain_bar;
+  using SP = SmemPlan<128, 1, 2, true, false>;
+  static unsigned long long attr_devs = 0;
+  if (dev >= 64 || !(attr_devs & (1ull << dev))) {
+    cudaError_t e = cudaFuncSetAttribute(umma_chain_kernel<128, 1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::kTotal);
+    if (e != cudaSuccess) return e;
+    if (dev < 64) attr_devs |= 1ull << dev;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = SP::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  at[na].id = cudaLaunchAttributeClusterDimension;
+  at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+  ++na;
+  if (pdl_take(c)) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  c->launch_count++;
+  return cudaLaunchKernelEx(&cfg, umma_chain_kernel<128, 1, 2, true>, P);
+}
+
+cudaError_t umma_run_op(Ctx* c, ConvOp& op, int n, float* out_ab_fused, float out_mult, cudaStream_t st, int img0,
+                        int max_ctas) {
+  UmmaPlan* pl = static_cast<UmmaPlan*>(op.umma_plan);
+  if (!pl) return cudaErrorInvalidValue;
+  UmmaParams prm;
+  cudaError_t pe = umma_prepare(c, op, n, out_ab_fused, out_mult, img0, max_ctas, prm);
+  if (pe != cudaSuccess) return pe;
   c->launch_count++;
   const bool split = !c->fast;
   const bool pdl = pdl_take(c);
