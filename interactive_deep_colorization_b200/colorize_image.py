@@ -69,8 +69,10 @@ class ColorizeImageBase(object):
                 print('I need to have %s!' % what)
                 return -1
         self.input_ab, self.input_mask = input_ab, input_mask
-        self.input_ab_mc = (input_ab - self.ab_mean) / self.ab_norm
-        self.input_mask_mult = input_mask * self.mask_mult
+        # reference :92-93.  With the PyTorch constants (ab_mean 0, ab_norm 1, mask_mult 1) both statements are exact
+        # identities; skipping the two float64 temporaries (2.5 MB of numpy traffic) is worth ~0.1 ms per click
+        self.input_ab_mc = input_ab if (self.ab_mean == 0 and self.ab_norm == 1) else (input_ab - self.ab_mean) / self.ab_norm
+        self.input_mask_mult = input_mask if self.mask_mult == 1 else input_mask * self.mask_mult
         return 0
 
     def get_result_PSNR(self, result=-1, return_SE_map=False):

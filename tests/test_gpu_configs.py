@@ -148,6 +148,7 @@ def test_plan_options_agree(synth_sd):
     ref = g["mc1_rand5_ab_raw"]
     outs = {}
     for name, opts in (("default", {}), ("no_pdl", {"pdl": 0}), ("no_side_dist", {"side_dist": 0}),
+                       ("chain", {"chain": 1}), ("prologue_sync2", {"prologue_sync2": 1}),
                        ("no_split_pairs", {"split_pairs": 0}), ("split_bn256", {"split_bn128": 0}),
                        ("no_halo", {"halo": 0}), ("halo_all", {"halo": 3})):
         ctx = util.make_ctx(synth_sd, 256, 256, max_n=1, dist=True, options=opts)
@@ -159,7 +160,7 @@ def test_plan_options_agree(synth_sd):
         assert err <= TOL_AB, (name, err)
         outs[name] = r
         ctx.close()
-    for k in ("no_pdl", "no_side_dist"):                               # scheduling only: bit-identical
+    for k in ("no_pdl", "no_side_dist", "chain", "prologue_sync2"):    # scheduling only: bit-identical
         assert np.array_equal(outs["default"]["ab"], outs[k]["ab"]), k
         assert np.array_equal(outs["default"]["dist"], outs[k]["dist"]), k
         assert np.array_equal(outs["default"]["rgb"], outs[k]["rgb"]), k

@@ -31,9 +31,9 @@ def main(specs):
         r2 = ctx.forward_host(L1, a1, m1, 0.5, want_dist=True, want_rgb=True)
         if base is None:
             base = r
-        print("[%s] max|d ab| vs reference golden %.3e   vs default plan %.3e   dist vs default %.3e   replay identical %s"
+        print("[%s] max|d ab| vs reference golden %.3e   vs default plan %.3e   dist vs default %.3e   replay identical %s   launches %d"
               % (name, util.maxabs(r["ab"][0], ref), util.maxabs(r["ab"], base["ab"]), util.maxabs(r["dist"], base["dist"]),
-                 bool(np.array_equal(r["ab"], r2["ab"]))))
+                 bool(np.array_equal(r["ab"], r2["ab"])), ctx.last_launch_count()))
         ctx.close()
 
 
