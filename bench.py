@@ -13,8 +13,10 @@ A step = ONE forward of the hot path (pack+conv1_1 -> conv trunk -> regression h
            timed region).
   config4  BASELINE config 4 as an extra record at every --gpus N: 512x512, GLOBAL batch 16 with a global-hints
            vector per image, sharded 16/N per GPU (strong scaling: 1 vs 8 GPUs).
-  latency  BASELINE config 5 (20 sequential put_point -> forward, dist head on): p50/p99 of the C-ABI click call and
-           of the wrapper-level calls the GUI makes (ui/gui_draw.py:258-286).
+  latency  BASELINE config 5 (20 sequential put_point -> forward, dist head on): p50/p99 of the complete click at the
+           C ABI (announced click: forward + the clicked pixel's pmf + 9 colour suggestions from ONE graph launch), the
+           round-2 protocol next to it (unannounced_*), and the wrapper-level calls the GUI makes (ui/gui_draw.py:258-286)
+           with two separate models and with the launcher's shared trunk.
 Every rank also runs ONE fixed-seed image outside the timed region; rank 0 asserts that all ranks produced the same
 bytes (the rank != 0 weight path: reserve -> broadcast -> adopt).
 The reference arm times the UNMODIFIED reference wrapper `ColorizeImageTorch.net_forward` (staged by
