@@ -203,7 +203,7 @@ class ColorizeImageB200(ColorizeImageBase):
         self._click(ctx, float(self.mask_cent))
         return self.output_rgb
 
-    def _click(self, ctx, maskcent, glob=None, mask_div=1.0, want_rgb=True):
+    def _click(self, ctx, maskcent, glob=None, mask_div=1.0, want_rgb=True, publish_rgb=None):
         """Stage the reference's float64 arrays into the context's page-locked click buffers (the float64 -> float32
         conversion IS the only CPU copy; L is re-staged only when the image changed), run idc_forward_host_q with
         the pinned buffers (zero-copy graph path) and publish copies of the results as the reference's attributes."""
@@ -228,7 +228,7 @@ class ColorizeImageB200(ColorizeImageBase):
                                  out_abq=buf["out_abq"] if want_q else None)
             ctx._wrapper_last = (float(maskcent), float(mask_div), glob is not None, bool(want_rgb), want_q)
         self.output_ab_raw = r["ab"][0].copy()   # raw net output (the parity quantity)
-        if want_rgb:
+        if want_rgb and (publish_rgb is None or publish_rgb):
             self.output_rgb = r["rgb"][0].copy()
             if want_q:
                 self.output_ab = r["abq"][0].copy()
@@ -443,8 +443,9 @@ class ColorizeImageB200Dist(ColorizeImageB200):
             self.output_ab_raw = r["ab"][0]
         else:
             ctx.set_dist_resident(True)                      # dist stays in HBM; pixels are fetched on demand
-            # on a shared context keep the colour model's graph (same outputs requested -> no re-capture)
-            self._click(ctx, float(self.mask_cent), want_rgb=getattr(self, "_trunk", None) is not None)
+            # on a shared context keep the colour model's graph (same outputs requested -> no re-capture); the
+            # distribution model itself publishes no RGB (reference :297-320 never sets output_rgb)
+            self._click(ctx, float(self.mask_cent), want_rgb=getattr(self, "_trunk", None) is not None, publish_rgb=False)
         if self.materialize_full:
             self.dist_ab = np.repeat(np.repeat(self.dist_ab_64, 4, axis=1), 4, axis=2)
             self.dist_ab_full = np.zeros((self.AB, self.Xd, self.Xd))

@@ -547,14 +547,17 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
     c->gadd_active = true;
   }
   const size_t HW = (size_t)c->H * c->W;
+  const bool c11_umma = c->opt.conv1_1_umma && !c->simt && c->w11_umma;
   if (hp) {
     for (int k = 0; k < hp->nchunks; ++k) {
       CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_in[k], 0));
       pdl_break(c);
-      CUDA_TRY(c, launch_conv1_1(c, hp->start[k + 1] - hp->start[k], L, ab, mask, maskcent, st, hp->start[k]));
+      if (c11_umma) CUDA_TRY(c, launch_conv1_1_umma(c, hp->start[k + 1] - hp->start[k], L, ab, mask, maskcent, st, hp->start[k]));
+      else CUDA_TRY(c, launch_conv1_1(c, hp->start[k + 1] - hp->start[k], L, ab, mask, maskcent, st, hp->start[k]));
     }
   } else {
-    CUDA_TRY(c, launch_conv1_1(c, n, L, ab, mask, maskcent, st));
+    if (c11_umma) CUDA_TRY(c, launch_conv1_1_umma(c, n, L, ab, mask, maskcent, st));
+    else CUDA_TRY(c, launch_conv1_1(c, n, L, ab, mask, maskcent, st));
   }
   mark();
   // Interactive batches: the dist head (class 1x1 conv + 529-way softmax) only depends on conv8_3, and decoder levels
@@ -692,11 +695,11 @@ int idc_set_option(idc_ctx* c, const char* name, int value) {
       {"halo", &c->opt.halo}, {"pairs", &c->opt.pairs}, {"mt", &c->opt.mt}, {"chunk_kb", &c->opt.chunk_kb},
       {"split_k", &c->opt.split_k}, {"direct_stores", &c->opt.direct_stores}, {"host_pipe", &c->opt.host_pipe},
       {"pdl", &c->opt.pdl}, {"split_pairs", &c->opt.split_pairs}, {"tanh_scale", &c->opt.tanh_scale},
-      {"side_dist", &c->opt.side_dist}, {"split_bn128", &c->opt.split_bn128}, {"halo_split", &c->opt.halo_split}, {"prologue_sync2", &c->opt.prologue_sync2}, {"chain", &c->opt.chain}};
+      {"side_dist", &c->opt.side_dist}, {"split_bn128", &c->opt.split_bn128}, {"halo_split", &c->opt.halo_split}, {"prologue_sync2", &c->opt.prologue_sync2}, {"chain", &c->opt.chain}, {"conv1_1_umma", &c->opt.conv1_1_umma}};
   for (auto& t : tab)
     if (!strcmp(t.n, name)) {
       *t.v = value;
-      if (c->weights_ready && strcmp(name, "host_pipe") && strcmp(name, "tanh_scale") && strcmp(name, "side_dist")) {      // plan-time option changed after planning: re-plan
+      if (c->weights_ready && strcmp(name, "host_pipe") && strcmp(name, "tanh_scale") && strcmp(name, "side_dist") && strcmp(name, "conv1_1_umma")) {      // plan-time option changed after planning: re-plan
         CUDA_TRY(c, cudaSetDevice(c->dev));
         CUDA_TRY(c, cudaDeviceSynchronize());
         int rc = plan_engines(c);
@@ -764,6 +767,7 @@ int idc_adopt_weights(idc_ctx* c) {
   // conv1_1 takes its weights as a kernel parameter: read them back from the (possibly received) arena
   CUDA_TRY(c, cudaMemcpy(c->h_w11.w, c->w11, sizeof(c->h_w11.w), cudaMemcpyDeviceToHost));
   CUDA_TRY(c, cudaMemcpy(c->h_w11.b, c->b11, sizeof(c->h_w11.b), cudaMemcpyDeviceToHost));
+  if (!c->simt) CUDA_TRY(c, conv1_1_umma_pack(c));      // tensor-core conv1_1: derived on the device, so ranks != 0 need nothing extra
   c->raw.clear();
   c->weights_ready = true;
   if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
@@ -1433,6 +1437,7 @@ int idc_destroy(idc_ctx* c) {
   if (c->splitk_ws) cudaFree(c->splitk_ws);
   if (c->splitk_counters) cudaFree(c->splitk_counters);
   if (c->chain_bar) cudaFree(c->chain_bar);
+  if (c->w11_umma) cudaFree(c->w11_umma);
   if (c->d_reccs) cudaFree(c->d_reccs);
   if (c->gvec) cudaFree(c->gvec);
   if (c->gtmp) cudaFree(c->gtmp);

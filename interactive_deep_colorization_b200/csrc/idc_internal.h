@@ -119,6 +119,7 @@ struct Options {
   int pdl = 1;            // programmatic dependent launch between the kernels of a forward
   int split_pairs = 1;    // cta_group::2 on the split-K (small batch) path
   int split_bn128 = 1;    // 128-column tiles on the split-K path (halves the partial-tile traffic of the reduction)
+  int conv1_1_umma = 1;   // model1.0 on the tensor cores (one padded k-block); 0 = the FP32 CUDA-core kernel
   int chain = 0;          // run consecutive same-shaped split-K layers as ONE launch with a grid barrier between layers
   int prologue_sync2 = 0; // pairs: second cluster barrier in the kernel prologue (before the TMEM allocation)
   int halo_split = 0;     // halo-tile A operand on the 128-column split-K path (stride-1 3x3 layers; experiment)
@@ -149,6 +150,7 @@ struct Ctx {
   float* w11 = nullptr;   // [36][64]  k = tap*4 + cin
   float* b11 = nullptr;   // [64]
   Conv11Weights h_w11;    // host copy passed by value to conv1_1_kernel
+  uint8_t* w11_umma = nullptr;   // conv1_1_umma_kernel: swizzled hi/lo weight tile + bias' / scale' (device, derived)
   float* wout = nullptr;  // [2][128]
   float* bout = nullptr;  // [2]
   // global hints MLP (device fp32)
@@ -224,6 +226,9 @@ cudaError_t umma_run_chain(Ctx* c, int first, int last, int n, cudaStream_t st);
 
 cudaError_t launch_conv1_1(Ctx* c, int n, const float* L, const float* ab, const float* mask,
                            float maskcent, cudaStream_t st, int img0 = 0);   // L/ab/mask: full arrays; images img0..img0+n
+cudaError_t launch_conv1_1_umma(Ctx* c, int n, const float* L, const float* ab, const float* mask, float maskcent,
+                                cudaStream_t st, int img0 = 0);              // the same layer on the tensor cores
+cudaError_t conv1_1_umma_pack(Ctx* c);                                       // weight tile for it, from the arena (device)
 cudaError_t launch_out_head(Ctx* c, int n, float* out_ab, cudaStream_t st);   // SIMT / KEEP_CONV10 path
 cudaError_t launch_softmax529(Ctx* c, int n, float* out_dist, cudaStream_t st);
 cudaError_t launch_lab2rgb(Ctx* c, int n, int h, int w, const float* L, float l_offset, const float* ab,

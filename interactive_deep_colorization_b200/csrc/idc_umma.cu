@@ -1067,6 +1067,251 @@ __global__ void __launch_bounds__(kThreads, 1) umma_chain_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------
+// conv1_1 on the tensor cores: the input pack cat(L/100, ab/110, mask - maskcent) (model.py:142-148) + model1.0
+// (4 -> 64, 3x3, ReLU; model.py:13-14) as ONE padded k-block.  K = 9 taps x 4 channels = 36 -> 48 (three K=16 steps).
+// There is no 16-byte granule to aim a TMA box at (a tap contributes 4 channels = 8 bytes), so the 128 threads of a CTA
+// gather and normalise their pixel's 36 inputs themselves, split them into FP16 hi / lo (x 2^6, like every activation)
+// and write their row of the two K-major SWIZZLE_128B operand tiles directly; the 64 x 48 weight tile (hi / lo,
+// pre-swizzled by conv1_1_pack_kernel) stays in shared memory for the life of the CTA.  9 MMAs (lo*hi, hi*lo, hi*hi per
+// K step) replace 2304 FFMAs per pixel; the epilogue (bias, ReLU, hi/lo split, warp-transposed stores) is the FP32
+// kernel's.  4 CTAs per SM hide each other's gather / MMA / epilogue phases (no intra-CTA pipeline).
+// ------------------------------------------------------------------------------------------
+constexpr int kC11K = 48;                       // padded K (3 MMA steps of 16)
+constexpr int kC11PackBytes = 2 * 8192 + 2 * 64 * 4;   // [B hi | B lo] smem images + bias' + scale'
+constexpr int kC11Smem = 2 * 16384 + kC11PackBytes + 64 + 1024;   // A hi/lo, pack, barrier + tmem ptr, alignment slack
+
+__device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {   // byte offset of a 16-byte chunk in a K-major SW128 tile
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+// one thread per output channel: power-of-two scale so the largest weight lands in [256, 512), hi/lo split, swizzled
+// smem image of the [64 cout][48 k] tile (k = tap * 4 + cin, zero beyond 36), bias' = bias * 2^6 * 2^e, scale' = 2^-e
+__global__ void conv1_1_pack_kernel(const float* __restrict__ w36x64, const float* __restrict__ bias, uint8_t* __restrict__ out) {
+  const int co = threadIdx.x;
+  if (co >= 64) return;
+  float mx = 0.f;
+  for (int k = 0; k < 36; ++k) mx = fmaxf(mx, fabsf(w36x64[k * 64 + co]));
+  int e = 0;
+  if (mx > 0.f) { int ex; frexpf(mx, &ex); e = 9 - ex; }        // mx * 2^e in [256, 512)
+  const float sc = ldexpf(1.f, e);
+  __half* bh = reinterpret_cast<__half*>(out);
+  __half* bl = reinterpret_cast<__half*>(out + 8192);
+  for (int k = 0; k < 64; ++k) {
+    const float v = k < 36 ? w36x64[k * 64 + co] * sc : 0.f;
+    __half hi, lo;
+    split_h(v, hi, lo);
+    const uint32_t o = (sw128_off(co, k >> 3) >> 1) + (k & 7);
+    bh[o] = hi; bl[o] = lo;
+  }
+  float* vec = reinterpret_cast<float*>(out + 16384);
+  vec[co] = bias[co] * kActScale * sc;
+  vec[64 + co] = ldexpf(1.f, -e);
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(128, 4)
+conv1_1_umma_kernel(const uint8_t* __restrict__ pack, const float* __restrict__ L, const float* __restrict__ ab,
+                    const float* __restrict__ mask, float maskcent, int N, int H, int Wd, __half* __restrict__ ohi,
+                    __half* __restrict__ olo, int* err) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_ahi = smem;                       // [128 px][64 k] FP16, K-major SW128 (16 KB); reused as the store staging
+  uint8_t* s_alo = smem + 16384;
+  uint8_t* s_pack = smem + 32768;              // B hi (8 KB) | B lo (8 KB) | bias' | scale'
+  const float* s_vec = reinterpret_cast<const float*>(s_pack + 16384);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pack + kC11PackBytes);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- setup: barrier, 64 TMEM columns, the packed weight tile ----
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(s_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(64u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(pack);
+    uint4* dst = reinterpret_cast<uint4*>(s_pack);
+    for (int i = threadIdx.x; i < kC11PackBytes / 16; i += 128) dst[i] = __ldg(src + i);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the weight tile is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  const size_t HW = (size_t)H * Wd, total = (size_t)N * HW;
+  const int ntiles = (int)((total + 127) / 128);
+  constexpr uint32_t idesc = make_idesc(64, kBM);
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const size_t pix = (size_t)tile * 128 + threadIdx.x;
+    const bool live = pix < total;
+    const size_t pixc = live ? pix : 0;
+    const int n = (int)(pixc / HW);
+    const int r = (int)(pixc - (size_t)n * HW);
+    const int y = r / Wd, x = r - y * Wd;
+    // ---- gather + normalise + split: this thread's row of the A tiles (k = tap * 4 + channel) ----
+    float in[kC11K];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int iy = y + ky - 1, ix = x + kx - 1;
+        const bool ok = live && iy >= 0 && iy < H && ix >= 0 && ix < Wd;
+        const size_t o = (size_t)iy * Wd + ix;
+        const int t = (ky * 3 + kx) * 4;
+        // zero padding applies to the concatenated, normalised input (model.py:148 then Conv2d pad)
+        const float l = ok ? __ldg(L + (size_t)n * HW + o) : 0.f;
+        const float a = ok ? __ldg(ab + (size_t)n * 2 * HW + o) : 0.f;
+        const float b = ok ? __ldg(ab + (size_t)n * 2 * HW + HW + o) : 0.f;
+        const float m = ok ? __ldg(mask + (size_t)n * HW + o) - maskcent : 0.f;
+        const float ql = l * 0.01f, qa = a * (1.0f / 110.0f), qb = b * (1.0f / 110.0f);
+        in[t + 0] = fmaf(fmaf(-ql, 100.0f, l), 0.01f, ql);                    // x / 100, correctly rounded (cf. div_corrected)
+        in[t + 1] = fmaf(fmaf(-qa, 110.0f, a), 1.0f / 110.0f, qa);
+        in[t + 2] = fmaf(fmaf(-qb, 110.0f, b), 1.0f / 110.0f, qb);
+        in[t + 3] = m;
+      }
+#pragma unroll
+    for (int k = 36; k < kC11K; ++k) in[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kC11K / 8; ++j) {
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float v0 = in[8 * j + 2 * q] * kActScale, v1 = in[8 * j + 2 * q + 1] * kActScale;
+        hw[q] = pack_f16x2_sat(v0, v1);
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[q]));
+        lw[q] = pack_f16x2_sat(v0 - hf.x, v1 - hf.y);
+      }
+      const uint32_t o = sw128_off(threadIdx.x, j);
+      st_shared_v4(smem_u32(s_ahi) + o, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+      if (SPLIT) st_shared_v4(smem_u32(s_alo) + o, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+    __syncthreads();
+    // ---- 9 MMAs into 64 TMEM columns: the small cross terms first, then hi*hi (as in umma_conv_kernel) ----
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t a_hi = make_sw128_desc(smem_u32(s_ahi)), a_lo = make_sw128_desc(smem_u32(s_alo));
+        const uint64_t b_hi = make_sw128_desc(smem_u32(s_pack)), b_lo = make_sw128_desc(smem_u32(s_pack) + 8192);
+        uint32_t first = 0u;
+        if (SPLIT) {
+#pragma unroll
+          for (int kk = 0; kk < kC11K / 16; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 2);
+            umma_f16(tmem, a_lo + adv, b_hi + adv, idesc, first);
+            umma_f16(tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+            first = 1u;
+          }
+        }
+#pragma unroll
+        for (int kk = 0; kk < kC11K / 16; ++kk) {
+          const uint64_t adv = (uint64_t)(kk * 2);
+          umma_f16(tmem, a_hi + adv, b_hi + adv, idesc, first);
+          first = 1u;
+        }
+        umma_commit(smem_u32(s_bar));
+      }
+      __syncwarp();
+    }
+    mbar_wait(smem_u32(s_bar), phase, err, 9);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: row = pixel; relu(acc + bias') * scale' = 2^6 * relu(conv + b) -> hi / lo -> coalesced stores ----
+    uint32_t v0[32], v1[32];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    tmem_ld32(taddr, v0);
+    tmem_ld32(taddr + 32, v1);
+    tmem_ld_wait();
+    tc_fence_before();
+    float f[64];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      f[c] = fmaxf(__uint_as_float(v0[c]) + s_vec[c], 0.f) * s_vec[64 + c];
+      f[32 + c] = fmaxf(__uint_as_float(v1[c]) + s_vec[32 + c], 0.f) * s_vec[96 + c];
+    }
+    // the operand tiles are consumed (the commit has arrived): reuse their memory as the per-warp transpose tiles
+    uint4* tilew = reinterpret_cast<uint4*>(s_ahi) + warp * 256;     // 32 rows x 8 chunks of 16 B = 4 KB per warp
+    const size_t wpix0 = (size_t)tile * 128 + warp * 32;
+#pragma unroll
+    for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane) {
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a0 = f[c8 * 8 + 2 * q], a1 = f[c8 * 8 + 2 * q + 1];
+          const uint32_t hw = pack_f16x2_sat(a0, a1);
+          if (plane == 0) {
+            w4[q] = hw;
+          } else {
+            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw));
+            w4[q] = pack_f16x2_sat(a0 - hf.x, a1 - hf.y);
+          }
+        }
+        tilew[lane * 8 + (c8 ^ (lane & 7))] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+      __syncwarp();
+      __half* gbase = (plane == 0 ? ohi : olo) + wpix0 * 64;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rl = i * 4 + (lane >> 3), c = lane & 7;
+        if (wpix0 + rl < total) reinterpret_cast<uint4*>(gbase)[i * 32 + lane] = tilew[rl * 8 + (c ^ (rl & 7))];
+      }
+      __syncwarp();
+    }
+    __syncthreads();        // TMEM drained and staging read by every warp before the next tile overwrites either
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u) : "memory");
+}
+
+cudaError_t conv1_1_umma_pack(Ctx* c) {
+  if (!c->w11_umma) {
+    cudaError_t e = cudaMalloc(&c->w11_umma, kC11PackBytes);
+    if (e != cudaSuccess) return e;
+  }
+  conv1_1_pack_kernel<<<1, 64>>>(c->w11, c->b11, c->w11_umma);
+  cudaError_t e = cudaGetLastError();
+  return e != cudaSuccess ? e : cudaDeviceSynchronize();
+}
+
+cudaError_t launch_conv1_1_umma(Ctx* c, int n, const float* L, const float* ab, const float* mask, float maskcent,
+                                cudaStream_t st, int img0) {
+  const ActBuf& o = c->bufs[c->buf_index.at("a1_1")];
+  const size_t HW = (size_t)o.H * o.W, npix = (size_t)n * HW, ooff = (size_t)img0 * HW * o.C;
+  const int ntiles = (int)((npix + 127) / 128);
+  static int sms[64] = {};
+  int& nsm = sms[c->dev < 64 ? c->dev : 0];
+  if (!nsm) { cudaDeviceProp prop; cudaGetDeviceProperties(&prop, c->dev); nsm = prop.multiProcessorCount; }
+  const int grid = ntiles < 4 * nsm ? ntiles : 4 * nsm;
+  L += img0 * HW; ab += img0 * 2 * HW; mask += img0 * HW;
+  static unsigned long long attr_devs = 0;
+  if (c->dev >= 64 || !(attr_devs & (1ull << c->dev))) {
+    cudaError_t e = cudaFuncSetAttribute(conv1_1_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC11Smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv1_1_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC11Smem);
+    if (e != cudaSuccess) return e;
+    if (c->dev < 64) attr_devs |= 1ull << c->dev;
+  }
+  __half* hi = static_cast<__half*>(o.p0) + ooff;
+  __half* lo = o.p1 ? static_cast<__half*>(o.p1) + ooff : nullptr;
+  cudaError_t e = lo ? launch_k(c, conv1_1_umma_kernel<true>, dim3(grid), dim3(128), (size_t)kC11Smem, st, c->w11_umma, L, ab, mask,
+                                maskcent, n, o.H, o.W, hi, lo, c->d_err)
+                     : launch_k(c, conv1_1_umma_kernel<false>, dim3(grid), dim3(128), (size_t)kC11Smem, st, c->w11_umma, L, ab, mask,
+                                maskcent, n, o.H, o.W, hi, lo, c->d_err);
+  c->launch_count++;
+  return e;
+}
+
+// ------------------------------------------------------------------------------------------
 // host side: tensor maps + launch plan
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -149,6 +149,7 @@ def test_plan_options_agree(synth_sd):
     outs = {}
     for name, opts in (("default", {}), ("no_pdl", {"pdl": 0}), ("no_side_dist", {"side_dist": 0}),
                        ("chain", {"chain": 1}), ("prologue_sync2", {"prologue_sync2": 1}),
+                       ("conv1_1_fp32", {"conv1_1_umma": 0}),
                        ("no_split_pairs", {"split_pairs": 0}), ("split_bn256", {"split_bn128": 0}),
                        ("no_halo", {"halo": 0}), ("halo_all", {"halo": 3})):
         ctx = util.make_ctx(synth_sd, 256, 256, max_n=1, dist=True, options=opts)
@@ -164,7 +165,7 @@ def test_plan_options_agree(synth_sd):
         assert np.array_equal(outs["default"]["ab"], outs[k]["ab"]), k
         assert np.array_equal(outs["default"]["dist"], outs[k]["dist"]), k
         assert np.array_equal(outs["default"]["rgb"], outs[k]["rgb"]), k
-    for k in ("no_split_pairs", "split_bn256", "no_halo", "halo_all"):
+    for k in ("no_split_pairs", "split_bn256", "no_halo", "halo_all", "conv1_1_fp32"):
         assert util.maxabs(outs[k]["ab"], outs["default"]["ab"]) < 3e-4, k
     # batch 4 on a max_n = 4 context (halo + pairs plans differ from the batch-1 context)
     L, ab, m = synth.synthetic_batch(4, 256, seed=77, max_hints=6)
