@@ -3,7 +3,7 @@
 tensor-core conv1_1, 128-column split-K pairs, chained launch on the second context) at 64x64 -- small enough for
 memcheck / racecheck to finish in minutes.
 
-    compute-sanitizer --tool memcheck python tools/sanitizer_click.py
+    compute-sanitizer --tool memcheck python tools/sanitizer_click.py [size] [opt:val,...]
 """
 import os
 import sys
@@ -17,11 +17,13 @@ from oracle import synth  # noqa: E402
 from tests import util  # noqa: E402
 
 X = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+EXTRA = {kv.split(":")[0]: int(kv.split(":")[1]) for kv in (sys.argv[2].split(",") if len(sys.argv) > 2 else []) if kv}
 sd = synth.torch_state_dict(1234)
 L, ab, m = synth.synthetic_batch(1, X, seed=0, max_hints=0)
 ab, m = ab.copy(), m.copy()
 outs = []
 for opts in ({}, {"chain": 1}):
+    opts = dict(opts, **EXTRA)
     ctx = util.make_ctx(sd, X, X, max_n=1, dist=True, options=opts)
     ctx.set_dist_resident(True)
     buf = ctx.click_buffers(1)
