@@ -121,7 +121,8 @@ struct Options {
   int split_bn128 = 1;    // 128-column tiles on the split-K path (halves the partial-tile traffic of the reduction)
   int conv1_1_umma = 1;   // model1.0 on the tensor cores (one padded k-block); 0 = the FP32 CUDA-core kernel
   int chain = 0;          // run consecutive same-shaped split-K layers as ONE launch with a grid barrier between layers
-  int prologue_sync2 = 0; // pairs: second cluster barrier in the kernel prologue (before the TMEM allocation)
+  int prologue_sync2 = 1; // pairs: cluster barrier between barrier init and the cta_group::2 TMEM allocation (0: -3 us per click,
+                          // bit-identical results, but compute-sanitizer racecheck flags the allocation -> kept on)
   int halo_split = 0;     // halo-tile A operand on the 128-column split-K path (stride-1 3x3 layers; experiment)
   int side_dist = 1;      // batch <= 4: run the dist head (class + softmax) on a side stream next to levels 9-10
   int tanh_scale = 110;   // regression head: tanh * 110 (model.py:175); the Caffe deploy nets use 100

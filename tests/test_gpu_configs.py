@@ -148,7 +148,7 @@ def test_plan_options_agree(synth_sd):
     ref = g["mc1_rand5_ab_raw"]
     outs = {}
     for name, opts in (("default", {}), ("no_pdl", {"pdl": 0}), ("no_side_dist", {"side_dist": 0}),
-                       ("chain", {"chain": 1}), ("prologue_sync2", {"prologue_sync2": 1}),
+                       ("chain", {"chain": 1}), ("prologue_sync1", {"prologue_sync2": 0}),
                        ("conv1_1_fp32", {"conv1_1_umma": 0}),
                        ("no_split_pairs", {"split_pairs": 0}), ("split_bn256", {"split_bn128": 0}),
                        ("no_halo", {"halo": 0}), ("halo_all", {"halo": 3})):
@@ -161,7 +161,7 @@ def test_plan_options_agree(synth_sd):
         assert err <= TOL_AB, (name, err)
         outs[name] = r
         ctx.close()
-    for k in ("no_pdl", "no_side_dist", "chain", "prologue_sync2"):    # scheduling only: bit-identical
+    for k in ("no_pdl", "no_side_dist", "chain", "prologue_sync1"):    # scheduling only: bit-identical
         assert np.array_equal(outs["default"]["ab"], outs[k]["ab"]), k
         assert np.array_equal(outs["default"]["dist"], outs[k]["dist"]), k
         assert np.array_equal(outs["default"]["rgb"], outs[k]["rgb"]), k
