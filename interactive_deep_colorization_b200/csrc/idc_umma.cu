@@ -811,9 +811,14 @@ __device__ __forceinline__ void conv_body(const CUtensorMap* bhi_list, const CUt
         // workspace layout [work item][column quad][row] (float4): lanes = rows -> 512-byte coalesced
         // pairs: each CTA of the pair parks / reduces its own 128 rows (slot = work item * CG + rank)
         float4* wp = reinterpret_cast<float4*>(p.ws) + ((size_t)(w * CG + (int)cta_rank) * (MT * BN / 4) + t_base / 4) * kBM + row;
+        // kSkipOwn (<= 64 accumulators per thread, i.e. the 128-column tiles): the pieces this CTA finishes itself stay
+        // in registers -- 1/S of the park traffic and one slice of the reduction reads less
+        constexpr bool kSkipOwn = CH <= 64;
 #pragma unroll
-        for (int j = 0; j < CH; j += 4)
+        for (int j = 0; j < CH; j += 4) {
+          if (kSkipOwn && ((c_base + j) >> 5) % S == ks) continue;
           __stcg(wp + (size_t)(j / 4) * kBM, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+        }
         __threadfence();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
@@ -831,26 +836,32 @@ __device__ __forceinline__ void conv_body(const CUtensorMap* bhi_list, const CUt
 #pragma unroll
         for (int ch = 0; ch < CH; ch += 32) {
           if (((c_base + ch) >> 5) % S != ks) continue;
+          // kSkipOwn: the accumulator already holds this CTA's own slice; the other slices are added to it in slice
+          // order (the order is a function of (piece, S) only, so results stay deterministic)
+          if (!kSkipOwn) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[ch + j] = 0.f;
+            for (int j = 0; j < 32; ++j) acc[ch + j] = 0.f;
+          }
           // The slices are summed in slice order (deterministic, same order as a serial loop), but the loads of QB
           // slices are issued together: a serial loop pays one L2 round trip (~700 cycles) per slice -- measured
           // 9 of the 10.3 kcycles this section took per launch at batch 1 (profiles/r02_cta_counters_batch1.txt).
-          constexpr int QB = (CH >= 128) ? 2 : 4;        // register budget: CH accumulators + QB * 32 in flight
+          constexpr int QB = kSkipOwn ? 3 : ((CH >= 128) ? 2 : 4);   // register budget: CH accumulators + QB * 32 in flight
           const float4* rp0 = reinterpret_cast<const float4*>(p.ws) +
                               ((size_t)(tile * S * CG + (int)cta_rank) * (MT * BN / 4) + (t_base + ch) / 4) * kBM + row;
           const size_t qstride = (size_t)CG * (MT * BN / 4) * kBM;
-          for (int q0 = 0; q0 < S; q0 += QB) {
+          const int n_other = kSkipOwn ? S - 1 : S;        // slices to fetch (kSkipOwn: all but this CTA's own)
+          for (int i0 = 0; i0 < n_other; i0 += QB) {
             float4 v[QB][8];
 #pragma unroll
             for (int qq = 0; qq < QB; ++qq) {
-              const int q = (q0 + qq < S) ? q0 + qq : q0;      // tail: re-read a valid slice, discarded below
+              const int i = (i0 + qq < n_other) ? i0 + qq : i0;      // tail: re-read a valid slice, discarded below
+              const int q = kSkipOwn ? i + (i >= ks ? 1 : 0) : i;
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[qq][j] = __ldcg(rp0 + (size_t)q * qstride + (size_t)j * kBM);
             }
 #pragma unroll
             for (int qq = 0; qq < QB; ++qq) {
-              if (q0 + qq < S) {
+              if (i0 + qq < n_other) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   acc[ch + 4 * j] += v[qq][j].x; acc[ch + 4 * j + 1] += v[qq][j].y;
