@@ -498,15 +498,18 @@ constexpr size_t kClickRes = (size_t)kClickInit * (3 * 32 + 2) * sizeof(double);
 constexpr size_t kClickCopy = kClickHdr + kClickPmf + kClickRes;         // what travels back per click
 constexpr size_t kClickBytes = kClickCopy + 529 * 2 * sizeof(float);     // + the default gamut grid (device only)
 
-// After the softmax of a small-batch forward: gather the clicked pixel's pmf, cluster it (K from the click header),
-// copy the block to pinned host memory.  Runs on the dist head's stream, i.e. off the critical path of the click.
-cudaError_t click_tail(Ctx* c, int n, const float* dist, cudaStream_t st) {
-  if (!c->click_mode || !c->d_clickout || n > 4) return cudaSuccess;
+// After the class conv of a small-batch forward: the clicked pixel's pmf straight from its 529 logits (same per-row
+// softmax routine as the full map, so the same bits), K-means on it (K from the click header), the block to pinned host
+// memory.  Runs next to the full-map softmax on a branch of the dist head's side branch.
+bool click_tail_on(Ctx* c, int n) { return c->click_mode && c->d_clickout && n <= 4; }
+
+cudaError_t click_tail(Ctx* c, int n, cudaStream_t st) {
+  if (!click_tail_on(c, n)) return cudaSuccess;
   int* hdr = reinterpret_cast<int*>(c->d_clickout);
   float* pmf = reinterpret_cast<float*>(c->d_clickout + kClickHdr);
   double* res = reinterpret_cast<double*>(c->d_clickout + kClickHdr + kClickPmf);
   const float* pts = reinterpret_cast<const float*>(c->d_clickout + kClickCopy);
-  cudaError_t e = launch_click_pmf(dist, c->d_click, n, c->H / 4, c->W / 4, hdr, pmf, st);
+  cudaError_t e = launch_click_pmf(c, c->d_click, n, hdr, pmf, st);
   if (e != cudaSuccess) return e;
   if ((e = launch_ab_reccs(pmf, 1, pts, 0, kClickMaxIter, kClickInit, res, st, hdr)) != cudaSuccess) return e;
   c->launch_count += 2;
@@ -591,8 +594,21 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
       CUDA_TRY(c, cudaStreamWaitEvent(c->s_side, c->ev_fork, 0));
       pdl_break(c);                                        // first kernel of the branch follows an event wait
       CUDA_TRY(c, umma_run_op(c, op, n, nullptr, (float)c->opt.tanh_scale, c->s_side, 0, 16));
+      const bool click = click_tail_on(c, n);
+      if (click) {   // idc_set_click: clicked pixel's pmf + suggestions only need the logits -> a branch of the branch
+        if (!c->s_click) {
+          CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_click, cudaStreamNonBlocking));
+          CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_click[0], cudaEventDisableTiming));
+          CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_click[1], cudaEventDisableTiming));
+        }
+        CUDA_TRY(c, cudaEventRecord(c->ev_click[0], c->s_side));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->s_click, c->ev_click[0], 0));
+        CUDA_TRY(c, click_tail(c, n, c->s_click));
+        CUDA_TRY(c, cudaEventRecord(c->ev_click[1], c->s_click));
+        if (cap != cudaStreamCaptureStatusActive) pdl_break(c);      // live stream: the record sits between class and softmax
+      }
       CUDA_TRY(c, launch_softmax529(c, n, out_dist, c->s_side));     // PDL-chained behind `class` on the side stream
-      CUDA_TRY(c, click_tail(c, n, out_dist, c->s_side));            // idc_set_click: clicked pixel's pmf + suggestions
+      if (click) CUDA_TRY(c, cudaStreamWaitEvent(c->s_side, c->ev_click[1], 0));
       CUDA_TRY(c, cudaEventRecord(c->ev_join, c->s_side));
       // in a capture the event record is not a node: up9 keeps its programmatic edge to c8_3; on a live stream the
       // record sits between the two kernels, so the next launch is serialised normally
@@ -625,7 +641,7 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
   if (!fused) CUDA_TRY(c, launch_out_head(c, n, out_ab, st));
   if (out_dist && !forked) {
     CUDA_TRY(c, launch_softmax529(c, n, out_dist, st));
-    CUDA_TRY(c, click_tail(c, n, out_dist, st));
+    CUDA_TRY(c, click_tail(c, n, st));
     pdl_break(c);
   }
   if (out_rgb) {
@@ -1457,6 +1473,7 @@ int idc_destroy(idc_ctx* c) {
   if (c->h_clickout) cudaFreeHost(c->h_clickout);
   if (c->dbg_ev[0]) { cudaEventDestroy(c->dbg_ev[0]); cudaEventDestroy(c->dbg_ev[1]); }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->s_click) { cudaStreamDestroy(c->s_click); cudaEventDestroy(c->ev_click[0]); cudaEventDestroy(c->ev_click[1]); }
   if (c->s_side) { cudaStreamDestroy(c->s_side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
   if (c->s_in) {
     cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);

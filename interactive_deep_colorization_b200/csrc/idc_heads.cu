@@ -192,6 +192,31 @@ cudaError_t launch_out_head(Ctx* c, int n, float* out_ab, cudaStream_t st) {
 // NCHW store is 128-byte coalesced.
 // ------------------------------------------------------------------------------------------
 constexpr int kBins = 529;
+// one warp, one pixel: v[j] = softmax(0.2 * logits)[lane + 32 j].  Shared by the full-map kernel and the click's
+// single-pixel kernel so that both produce the same bits (same instruction sequence, same reduction order).
+__device__ __forceinline__ void softmax529_row(const float* __restrict__ row, int lane, float (&v)[17]) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 17; ++j) {
+    const int ch = lane + 32 * j;
+    v[j] = ch < kBins ? row[ch] * 0.2f : -INFINITY;   // model.py:160 "* .2"
+    mx = fmaxf(mx, v[j]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 17; ++j) {
+    v[j] = (lane + 32 * j) < kBins ? expf(v[j] - mx) : 0.f;
+    sum += v[j];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int j = 0; j < 17; ++j) v[j] *= inv;
+}
+
 __global__ void __launch_bounds__(256) softmax529_kernel(const float* __restrict__ logits, int ld, int M, int HW4,
                                                          float* __restrict__ out) {
   extern __shared__ float tile[];  // [529][33]
@@ -202,30 +227,12 @@ __global__ void __launch_bounds__(256) softmax529_kernel(const float* __restrict
     const int pl = warp * 4 + q;
     const int p = p0 + pl;
     if (p >= M) continue;
-    const float* row = logits + (size_t)p * ld;
     float v[17];
-    float mx = -INFINITY;
+    softmax529_row(logits + (size_t)p * ld, lane, v);
 #pragma unroll
     for (int j = 0; j < 17; ++j) {
       const int ch = lane + 32 * j;
-      v[j] = ch < kBins ? row[ch] * 0.2f : -INFINITY;   // model.py:160 "* .2"
-      mx = fmaxf(mx, v[j]);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < 17; ++j) {
-      v[j] = (lane + 32 * j) < kBins ? expf(v[j] - mx) : 0.f;
-      sum += v[j];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.0f / sum;
-#pragma unroll
-    for (int j = 0; j < 17; ++j) {
-      const int ch = lane + 32 * j;
-      if (ch < kBins) tile[ch * 33 + pl] = v[j] * inv;
+      if (ch < kBins) tile[ch * 33 + pl] = v[j];
     }
   }
   __syncthreads();
@@ -660,22 +667,32 @@ __device__ __forceinline__ int block_argmax(double v, int idx, double* rv, int* 
 }
 
 // The click of the interactive path (idc_set_click): `click` = {img, y4, x4, K, seq, ...} in mapped host memory, read
-// when the graph RUNS (the graph itself never changes).  Copies dist[img, :, y4, x4] (529 floats) behind an 8-int
-// header that echoes the click, so the host can tell which pixel the block belongs to.
-__global__ void __launch_bounds__(544) click_pmf_kernel(const float* __restrict__ dist, const int* __restrict__ click,
-                                                        int n_img, int H4, int W4, int* __restrict__ out_hdr,
-                                                        float* __restrict__ out_pmf) {
+// when the graph RUNS (the graph itself never changes).  One warp computes the clicked pixel's softmax straight from the
+// class logits -- the same per-row routine as softmax529_kernel, so the 529 floats are bit-identical to
+// dist[img, :, y4, x4] without waiting for the full-map softmax -- behind an 8-int header that echoes the click, so the
+// host can tell which pixel the block belongs to.
+__global__ void __launch_bounds__(32) click_pmf_kernel(const float* __restrict__ logits, int ld, const int* __restrict__ click,
+                                                       int n_img, int H4, int W4, int* __restrict__ out_hdr,
+                                                       float* __restrict__ out_pmf) {
+  const int lane = threadIdx.x;
   const int img = click[0], y4 = click[1], x4 = click[2];
   const bool ok = img >= 0 && img < n_img && y4 >= 0 && y4 < H4 && x4 >= 0 && x4 < W4;
-  if (threadIdx.x < 8) out_hdr[threadIdx.x] = threadIdx.x == 7 ? (ok ? 1 : 0) : click[threadIdx.x];
-  if (!ok || threadIdx.x >= kBins) return;
-  const size_t HW4 = (size_t)H4 * W4;
-  out_pmf[threadIdx.x] = dist[((size_t)img * kBins + threadIdx.x) * HW4 + (size_t)y4 * W4 + x4];
+  if (lane < 8) out_hdr[lane] = lane == 7 ? (ok ? 1 : 0) : click[lane];
+  if (!ok) return;
+  float v[17];
+  softmax529_row(logits + ((size_t)(img * H4 + y4) * W4 + x4) * ld, lane, v);
+#pragma unroll
+  for (int j = 0; j < 17; ++j) {
+    const int ch = lane + 32 * j;
+    if (ch < kBins) out_pmf[ch] = v[j];
+  }
 }
 
-cudaError_t launch_click_pmf(const float* dist, const int* click_dev, int n_img, int H4, int W4, int* out_hdr,
-                             float* out_pmf, cudaStream_t st) {
-  click_pmf_kernel<<<1, 544, 0, st>>>(dist, click_dev, n_img, H4, W4, out_hdr, out_pmf);
+cudaError_t launch_click_pmf(Ctx* c, const int* click_dev, int n_img, int* out_hdr, float* out_pmf, cudaStream_t st) {
+  int ld = 0;
+  for (auto& op : c->ops)
+    if (op.kind == OP_CLASS) ld = op.cout_pad;
+  click_pmf_kernel<<<1, 32, 0, st>>>(c->logits, ld, click_dev, n_img, c->H / 4, c->W / 4, out_hdr, out_pmf);
   return cudaGetLastError();
 }
 
@@ -721,13 +738,19 @@ __global__ void __launch_bounds__(1024) ab_reccs_kernel(const float* __restrict_
   }
   __syncthreads();
 
-  // greedy seeding
-  int rank = 0;
-  if (live)
-    for (int j = 0; j < kReccBins; ++j) rank += (w[j] > w[tid]) || (w[j] == w[tid] && j < tid);
+  // greedy seeding.  Restart v starts from the bin of weight-rank v (order: weight descending, index ascending):
+  // v + 1 arg-max rounds with the winners taken out, instead of ranking all 529 bins against each other
+  int first = 0;
+  {
+    bool taken = false;
+    for (int r = 0; r <= (int)blockIdx.x; ++r) {
+      first = block_argmax(live && !taken ? w[tid] : -1.0, live ? tid : 0x7fffffff, rv, ri);
+      taken = taken || tid == first;
+    }
+  }
   for (int j = 0; j < K; ++j) {
     double score = -1.0;
-    if (live) score = j == 0 ? (rank == (int)blockIdx.x ? 2.0 : -1.0) : w[tid] * mind[tid];
+    if (live) score = j == 0 ? (tid == first ? 2.0 : -1.0) : w[tid] * mind[tid];
     const int pick = block_argmax(score, live ? tid : 0x7fffffff, rv, ri);
     if (tid == 0) { cx[j] = px[pick]; cy[j] = py[pick]; }
     __syncthreads();

@@ -189,6 +189,8 @@ struct Ctx {
   // dist head off the critical path: class + softmax run on a side stream next to decoder levels 9-10
   cudaStream_t s_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t s_click = nullptr;            // announced click: pmf + suggestions next to the full-map softmax
+  cudaEvent_t ev_click[2] = {nullptr, nullptr};
   int image_n = 0;                           // idc_set_image: this many L planes are resident at the head of d_in
   cudaEvent_t ev_in[8] = {}, ev_out[8] = {};
   // CUDA graph cache for the batch-1 latency path
@@ -238,8 +240,7 @@ cudaError_t launch_decode313(Ctx* c, int n, float T, float* out_ab, cudaStream_t
 cudaError_t launch_dist313_pixel(Ctx* c, int img, int y, int x, float S, float* out313_dev, cudaStream_t st);
 cudaError_t launch_ab_reccs(const float* pmf, size_t bin_stride, const float* pts_dev, int K, int max_iter,
                             int n_init, double* out_dev, cudaStream_t st, const int* dyn = nullptr);
-cudaError_t launch_click_pmf(const float* dist, const int* click_dev, int n_img, int H4, int W4, int* out_hdr,
-                             float* out_pmf, cudaStream_t st);
+cudaError_t launch_click_pmf(Ctx* c, const int* click_dev, int n_img, int* out_hdr, float* out_pmf, cudaStream_t st);
 cudaError_t launch_global_stats(int h, int w, const uint8_t* rgb, const float* pts, float* out316, cudaStream_t st);
 cudaError_t launch_rgb2lab(int n, int h, int w, const uint8_t* rgb, double* lab, cudaStream_t st);
 cudaError_t launch_zoom_lab2rgb(const double* ab, int hin, int win, const double* Lfull, int H, int W, uint8_t* rgb,
