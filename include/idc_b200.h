@@ -132,6 +132,7 @@ int idc_forward(idc_ctx* ctx, int n, int h, int w, const float* L_mc, const floa
  * Batches <= 4 (the interactive click) replay ONE CUDA graph: a single H2D of the staged inputs, the kernels chained by
  * programmatic dependent launch, a single D2H of the results; batches >= 8 copy straight from / to pinned caller
  * buffers (pageable ones are staged) and overlap the copies with the first / last layer in image chunks.
+ * L_mc may be NULL when idc_set_image has made the n L planes resident (then only the hints travel).
  * Results are bit-identical to idc_forward. */
 int idc_forward_host(idc_ctx* ctx, int n, int h, int w, const float* L_mc, const float* ab,
                      const float* mask, float maskcent, const float* glob, float* out_ab,

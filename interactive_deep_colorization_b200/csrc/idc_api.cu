@@ -659,11 +659,11 @@ int run_forward(Ctx* c, int n, const float* L, const float* ab, const float* mas
 }
 
 int check_forward_args(Ctx* c, int n, int h, int w, const void* L, const void* ab, const void* mask, const void* glob,
-                       const void* out_ab, const void* out_dist) {
+                       const void* out_ab, const void* out_dist, bool resident_l_ok = false) {
   if (!c->weights_ready) return fail(c, IDC_ERR_STATE, "idc_forward before idc_finalize_weights");
   if (n < 1 || n > c->max_n) return fail(c, IDC_ERR_ARG, "n=%d outside [1,%d]", n, c->max_n);
   if (h != c->H || w != c->W) return fail(c, IDC_ERR_ARG, "geometry %dx%d != ctx geometry %dx%d", h, w, c->H, c->W);
-  if (!L || !ab || !mask || !out_ab) return fail(c, IDC_ERR_ARG, "null L/ab/mask/out_ab");   // L: see idc_set_image
+  if ((!L && !resident_l_ok) || !ab || !mask || !out_ab) return fail(c, IDC_ERR_ARG, "null L/ab/mask/out_ab");
   if (out_dist && !c->dist) return fail(c, IDC_ERR_ARG, "out_dist requires IDC_FLAG_DIST");
   if (glob && !c->glob) return fail(c, IDC_ERR_ARG, "glob requires IDC_FLAG_GLOBAL_HINTS");
   return IDC_OK;
@@ -982,7 +982,7 @@ int idc_forward_host_q(idc_ctx* c, int n, int h, int w, const float* L, const fl
                        float maskcent, const float* glob, float* out_ab, float* out_dist, uint8_t* out_rgb,
                        double* out_abq) {
   if (!c) return IDC_ERR_ARG;
-  int rc = check_forward_args(c, n, h, w, L ? (const void*)L : (const void*)c, ab, mask, glob, out_ab, out_dist);
+  int rc = check_forward_args(c, n, h, w, L, ab, mask, glob, out_ab, out_dist, /*resident_l_ok=*/true);   // NULL L: idc_set_image
   if (rc != IDC_OK) return rc;
   if (out_abq && !out_rgb) return fail(c, IDC_ERR_ARG, "out_abq (quantised ab) is derived from out_rgb: pass both");
   CUDA_TRY(c, cudaSetDevice(c->dev));
