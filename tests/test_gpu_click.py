@@ -103,6 +103,31 @@ def test_announced_click_returns_pmf_and_suggestions_with_the_forward(synth_sd):
     ctx.close(); plain.close()
 
 
+def test_announced_click_in_a_small_batch(synth_sd):
+    """The click may sit in any image of a graph-path batch (n <= 4); an image index outside the batch is answered by
+    the device path's own error, not by stale host data."""
+    X = 64
+    L, ab, m = synth.synthetic_batch(3, X, seed=21, max_hints=5)
+    ctx = util.make_ctx(synth_sd, X, X, max_n=3, dist=True)
+    ctx.set_dist_resident(True)
+    plain = util.make_ctx(synth_sd, X, X, max_n=3, dist=True)
+    plain.set_dist_resident(True)
+    plain.forward_host(L, ab, m, 0.5)
+    for img, y4, x4, K in ((0, 3, 5, 4), (2, 15, 0, 9), (1, 7, 7, 0)):
+        ctx.set_click(img, y4, x4, K)
+        r = ctx.forward_host(L, ab, m, 0.5)
+        assert np.array_equal(r["ab"], plain.forward_host(L, ab, m, 0.5)["ab"])
+        assert np.array_equal(ctx.fetch_dist(img, y4, x4), plain.fetch_dist(img, y4, x4))
+        if K:
+            a, b = ctx.ab_reccs(img, y4, x4, K=K), plain.ab_reccs(img, y4, x4, K=K)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    ctx.set_click(3, 1, 1, 5)                    # image 3 of a 3-image batch does not exist
+    ctx.forward_host(L, ab, m, 0.5)
+    with pytest.raises(_lib.IdcError):
+        ctx.fetch_dist(3, 1, 1)
+    ctx.close(); plain.close()
+
+
 def test_shared_trunk_pair_is_one_forward_per_click(synth_sd):
     """launcher --backend b200: colour model and distribution model share one context (ideepcolor.py:34-38 loads the
     same checkpoint into both).  Per click the pair must publish exactly what two separately prepared models publish,
