@@ -128,6 +128,34 @@ def test_announced_click_in_a_small_batch(synth_sd):
     ctx.close(); plain.close()
 
 
+def test_click_at_512_against_the_oracle(synth_sd):
+    """The interactive plan at the high-resolution size of BASELINE config 4 (512^2, batch 1: 64^2 bottleneck, other
+    split-K shapes than at 256^2): raw ab within tolerance of the oracle, dist normalised, announced click identical to
+    the plain lookups, graph replay identical."""
+    X = 512
+    L, ab, m = synth.synthetic_batch(1, X, seed=33, max_hints=8)
+    ctx = util.make_ctx(synth_sd, X, X, max_n=1, dist=True)
+    ctx.set_dist_resident(True)
+    reg, dist = util.oracle_forward(synth_sd, L, ab, m, 0.5, dist=True)
+    ctx.set_click(0, 70, 101, 9)
+    r = ctx.forward_host(L, ab, m, 0.5, want_rgb=True)
+    r2 = ctx.forward_host(L, ab, m, 0.5, want_rgb=True)
+    assert np.array_equal(r["ab"], r2["ab"]) and np.array_equal(r["rgb"], r2["rgb"])
+    err = util.maxabs(r["ab"], reg)
+    print("512^2 click: max|d ab| vs oracle = %.3e" % err)
+    assert err <= 1e-3
+    pmf = ctx.fetch_dist(0, 70, 101)
+    assert util.maxabs(pmf, dist.numpy()[0, :, 70, 101]) < 1e-5 and abs(float(pmf.sum()) - 1.0) < 1e-4
+    full = ctx.fetch_dist(0)
+    assert np.array_equal(full[:, 70, 101], pmf)
+    served = ctx.ab_reccs(0, 70, 101, K=9)
+    ctx.set_click(0, -1, 0, 0)
+    ctx.forward_host(L, ab, m, 0.5, want_rgb=True)
+    plain = ctx.ab_reccs(0, 70, 101, K=9)
+    assert np.array_equal(served[0], plain[0]) and np.array_equal(served[1], plain[1])
+    ctx.close()
+
+
 def test_shared_trunk_pair_is_one_forward_per_click(synth_sd):
     """launcher --backend b200: colour model and distribution model share one context (ideepcolor.py:34-38 loads the
     same checkpoint into both).  Per click the pair must publish exactly what two separately prepared models publish,

@@ -164,4 +164,6 @@ if __name__ == "__main__":
     specs = sys.argv[1:] or ["default="]
     for spec in specs:
         name, _, body = spec.partition("=")
-        run(name, {kv.split(":")[0]: int(kv.split(":")[1]) for kv in body.split(",") if kv})
+        opts = {kv.split(":")[0]: int(kv.split(":")[1]) for kv in body.split(",") if kv}
+        size = opts.pop("size", 256)               # size:512 = the high-resolution click
+        run(name, opts, X=size)
