@@ -27,10 +27,10 @@ for tag, opts in (("per-tap", {}), ("halo+resident", {"halo": 3})):
         ctx.forward_device(dL, dab, dm, 0.5)
     prof = dict((nm, ms) for nm, ms, _ in ctx.get_profile())
     ctx.set_profiling(False)
+    act = ctx.get_activation("conv1_2", min(n, 4)).cpu().numpy()
+    res[tag] = (act, out["ab"].cpu().numpy())
     print("batch %d %-14s c1_2 %.1f us   pack+conv1_1 %.1f   c2_1 %.1f   forward sum %.2f ms"
           % (n, tag, prof["c1_2"] * 1e3, prof["pack+conv1_1"] * 1e3, prof["c2_1"] * 1e3, sum(prof.values())))
-    act = ctx.get_activation("conv1_2", n)[:: max(1, n // 4)].cpu().numpy()      # a few images of the batch
-    res[tag] = (act, out["ab"].cpu().numpy())
     ctx.close()
 print("max|d conv1_2| = %.3e (max|conv1_2| %.2f)   max|d ab| = %.3e"
       % (float(np.abs(res["per-tap"][0] - res["halo+resident"][0]).max()), float(np.abs(res["per-tap"][0]).max()),
