@@ -326,13 +326,7 @@ struct SmemPlan {
   static constexpr int kTail = 3 * BN * 4 + 272 * 4 + 256 + 128 * 2 * 4;  // epi vecs, head, barriers, head reduce
   static constexpr int kOutStage = 16384;                         // epilogue staging: one private 2 KB transpose tile per accumulate warp
   static constexpr int kBudget = 232448 - 1024 - kTail - kOutStage - kHaloBytes;  // 227 KB opt-in limit minus alignment slack
-  // RESIDENT (64-column halo tiles as CTA pairs, i.e. conv1_2): the layer's whole weight matrix -- 9 k-blocks x 8 KB per
-  // CTA -- is loaded ONCE per CTA and stays in the ring; later tiles neither load nor wait for weights.  With a 4-stage
-  // ring of 8 KB stages the MMA warp starved on the round trips of those small loads.
-  static constexpr bool kResident = HALO && BN == 64 && CG == 2;
-  static constexpr int kResidentKb = 9;
-  static constexpr int kStages = kResident ? kResidentKb : (kBudget / kStageBytes >= 4 ? 4 : kBudget / kStageBytes);
-  static_assert(!kResident || kBudget / kStageBytes >= kResidentKb, "resident weights do not fit");
+  static constexpr int kStages = kBudget / kStageBytes >= 4 ? 4 : kBudget / kStageBytes;
   static constexpr int kTotal = kStages * kStageBytes + kHaloBytes + kOutStage + kTail + 1024;   // + alignment slack
   static constexpr int kBufCols = MT * BN;                       // TMEM columns of one chunk buffer
   static constexpr int kNBuf = (512 / kBufCols) >= 4 ? 4 : (512 / kBufCols);
@@ -373,9 +367,8 @@ __device__ __forceinline__ void conv_body(const CUtensorMap* bhi_list, const CUt
   uint64_t* tfull_bar = s_bar + 2 * STAGES;        // [NBUF]   MMA -> accumulate warps (chunk ready)
   uint64_t* tempty_bar = s_bar + 2 * STAGES + NBUF;  // [NBUF] accumulate warps -> MMA (chunk drained)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * STAGES + 2 * NBUF);
-  uint64_t* afull_bar = s_bar + 28;                // [2] HALO: halo TMA -> MMA   (2 * STAGES + 2 * NBUF + 1 <= 27)
-  uint64_t* aempty_bar = s_bar + 30;               // [2] HALO: MMA -> halo TMA
-  constexpr bool RESIDENT = SP::kResident;
+  uint64_t* afull_bar = s_bar + 20;                // [2] HALO: halo TMA -> MMA
+  uint64_t* aempty_bar = s_bar + 22;               // [2] HALO: MMA -> halo TMA
   float* s_red = reinterpret_cast<float*>(s_bar + 32);   // [128][2] fused-head partial sums, after the 256-byte barrier block
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -541,8 +534,8 @@ __device__ __forceinline__ void conv_body(const CUtensorMap* bhi_list, const CUt
               }
               __syncwarp();
             }
-            if (!RESIDENT) mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 1);
-            if (!RESIDENT && k >= kpre && elect_one()) {     // RESIDENT: the prefetch above loaded every weight tile, once
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 1);
+            if (k >= kpre && elect_one()) {
               const uint32_t fb = smem_u32(&full_bar[stage]);
               const int4 e = __ldg(kb + k);
               const uint32_t sb = smem_u32(smem + stage * SP::kStageBytes);
@@ -631,8 +624,7 @@ __device__ __forceinline__ void conv_body(const CUtensorMap* bhi_list, const CUt
               }
               hslot = (hcount - 1) & 1;
             }
-            if (!RESIDENT || w == (int)(blockIdx.x / CG))     // RESIDENT: weights arrive once, with the CTA's first tile
-              mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 3);
+            mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 3);
             if (IDC_CTA_COUNTERS && p.dbgbuf) {
               t_wait_full += clock64() - tB;
               if (t_first_full == 0) t_first_full = clock64() - t_kernel0;
@@ -681,7 +673,7 @@ __device__ __forceinline__ void conv_body(const CUtensorMap* bhi_list, const CUt
               }
             }
             if (PAIR) {
-              if (!RESIDENT) umma_commit_pair(smem_u32(&empty_bar[stage]));        // both CTAs' stages
+              umma_commit_pair(smem_u32(&empty_bar[stage]));                       // both CTAs' stages
               if (HALO && k % 9 == 8) umma_commit_pair(smem_u32(&aempty_bar[hslot]));   // both CTAs' halo slots
               if (k == k1 - 1) umma_commit_pair(smem_u32(&tfull_bar[buf]));        // both CTAs' accumulate warps
             } else {
@@ -1466,10 +1458,7 @@ int umma_plan_op(Ctx* c, ConvOp& op) {
   pl->cg = 1;
   {
     const long tiles1 = (long)op.ncls * c->max_n * ceil_div(op.Hl, op.hbox) * ceil_div(op.Wl, op.wbox) * (op.cout_pad / op.bn_tile);
-    // 64-column halo pairs keep the whole weight matrix resident (SmemPlan::kResident): exactly 9 k-blocks (Cin = 64)
-    const bool halo64_ok = !pl->halo || op.bn_tile != 64 || op.K / kBK == 9;
-    const bool can = !c->fast && halo64_ok &&
-                     (op.bn_tile == 256 || op.bn_tile == 128 || (op.bn_tile == 64 && (pl->mt == 2 || pl->halo)));
+    const bool can = !c->fast && (op.bn_tile == 256 || op.bn_tile == 128 || (op.bn_tile == 64 && (pl->mt == 2 || pl->halo)));
     const long tiles_mt = tiles1 / pl->mt;
     const int mode = c->opt.pairs;   // 0 = off, 1 (default) = launches that give every SM pair >= 2 tiles, 2 = always
     // >= 2 tiles per SM (= 4 per pair).  Measured at batch 1 (profiles/r02_latency_per_op.txt): up10 62 -> 55 us,
