@@ -20,6 +20,10 @@
 //   epilogue (TMEM chunk -> regs += ; at tile end bias/act/BN/global-hints -> hi/lo split -> NHWC
 //   store, or the fused model_out head).  Warp w owns TMEM lane quarter w%4 and column half (w-2)/4.
 //   Persistent grid = min(tiles, #SM).
+// * also in this file: CTA pairs (cta_group::2), the halo-tile A operand, deterministic split-K for launches that
+//   cannot fill the machine (128-column tiles; the CTA's own pieces never leave its registers), the chained launch
+//   (conv_body<..., CHAIN>: several layers, one launch, grid barrier) and conv1_1_umma_kernel (model1.0 as one padded
+//   k-block whose operand rows the threads write themselves).
 #include <stdio.h>
 #include <stdlib.h>
 
