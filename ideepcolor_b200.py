@@ -55,7 +55,9 @@ def main(argv=None):
     X = args.load_size
     sd = torch.load(args.color_model, map_location="cpu")
     color_model = CI.ColorizeImageB200(Xd=X, maskcent=args.pytorch_maskcent)
-    color_model.prep_net(gpu_id=args.gpu, state_dict=sd)
+    # one checkpoint, one trunk (ideepcolor.py:34-38 "same model used for both"): with suggestions on, the colour model
+    # carries the distribution head and the distribution model below shares its context -> ONE forward for both
+    color_model.prep_net(gpu_id=args.gpu, state_dict=sd, dist=args.suggest > 0)
     color_model.load_image(args.image_file)
 
     im_ab, im_mask = np.zeros((2, X, X)), np.zeros((1, X, X))
@@ -70,9 +72,9 @@ def main(argv=None):
     suggestions = None
     if args.suggest > 0 and hints:
         dist_model = CI.ColorizeImageB200Dist(Xd=X, maskcent=args.pytorch_maskcent)
-        dist_model.prep_net(gpu_id=args.gpu, state_dict=sd, dist=True)
+        dist_model.share_trunk(color_model)
         dist_model.set_image(color_model.img_rgb)
-        dist_model.net_forward(im_ab, im_mask)
+        dist_model.net_forward(im_ab, im_mask)          # answered from the colour model's forward above
         suggestions = []
         for h in hints:
             centers, conf = dist_model.get_ab_reccs(int(h["loc"][0]), int(h["loc"][1]), K=args.suggest, return_conf=True)
