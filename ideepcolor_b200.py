@@ -59,6 +59,10 @@ def main(argv=None):
     # carries the distribution head and the distribution model below shares its context -> ONE forward for both
     color_model.prep_net(gpu_id=args.gpu, state_dict=sd, dist=args.suggest > 0)
     color_model.load_image(args.image_file)
+    dist_model = None
+    if args.suggest > 0:
+        dist_model = CI.ColorizeImageB200Dist(Xd=X, maskcent=args.pytorch_maskcent)
+        dist_model.share_trunk(color_model)             # before the forward: it then carries the distribution head
 
     im_ab, im_mask = np.zeros((2, X, X)), np.zeros((1, X, X))
     hints = json.load(open(args.hints)) if args.hints else []
@@ -71,8 +75,6 @@ def main(argv=None):
 
     suggestions = None
     if args.suggest > 0 and hints:
-        dist_model = CI.ColorizeImageB200Dist(Xd=X, maskcent=args.pytorch_maskcent)
-        dist_model.share_trunk(color_model)
         dist_model.set_image(color_model.img_rgb)
         dist_model.net_forward(im_ab, im_mask)          # answered from the colour model's forward above
         suggestions = []

@@ -203,13 +203,14 @@ class ColorizeImageB200(ColorizeImageBase):
         self._click(ctx, float(self.mask_cent))
         return self.output_rgb
 
-    def _click(self, ctx, maskcent, glob=None, mask_div=1.0, want_rgb=True, publish_rgb=None):
+    def _click(self, ctx, maskcent, glob=None, mask_div=1.0, want_rgb=True, publish_rgb=None, need_dist=False):
         """Stage the reference's float64 arrays into the context's page-locked click buffers (the float64 -> float32
         conversion IS the only CPU copy; L is re-staged only when the image changed), run idc_forward_host_q with
         the pinned buffers (zero-copy graph path) and publish copies of the results as the reference's attributes."""
         buf = self._click_buffers(ctx, glob is not None)
         want_q = bool(want_rgb and self.gpu_prepost)
-        if ctx._wrapper_shared and glob is None and self._same_as_last_forward(ctx, buf, maskcent, mask_div, want_rgb, want_q):
+        if ctx._wrapper_shared and glob is None and \
+                self._same_as_last_forward(ctx, buf, maskcent, mask_div, want_rgb, want_q, need_dist):
             # share_trunk: the other model of the pair just ran this very forward; its results are still in the buffers
             r = {"ab": buf["out_ab"], "rgb": buf["out_rgb"], "abq": buf["out_abq"]}
         else:
@@ -226,7 +227,8 @@ class ColorizeImageB200(ColorizeImageBase):
             r = ctx.forward_host(None, buf["ab"], buf["mask"], maskcent, glob=buf["glob"], want_rgb=want_rgb,
                                  want_abq=want_q, out_ab=buf["out_ab"], out_rgb=buf["out_rgb"] if want_rgb else None,
                                  out_abq=buf["out_abq"] if want_q else None)
-            ctx._wrapper_last = (float(maskcent), float(mask_div), glob is not None, bool(want_rgb), want_q)
+            ctx._wrapper_last = (float(maskcent), float(mask_div), glob is not None, bool(want_rgb), want_q,
+                                 bool(getattr(ctx, "_dist_resident", False)))
         self.output_ab_raw = r["ab"][0].copy()   # raw net output (the parity quantity)
         if want_rgb and (publish_rgb is None or publish_rgb):
             self.output_rgb = r["rgb"][0].copy()
@@ -247,12 +249,12 @@ class ColorizeImageB200(ColorizeImageBase):
             ctx._wrapper_last = None
         return buf
 
-    def _same_as_last_forward(self, ctx, buf, maskcent, mask_div, want_rgb, want_q):
+    def _same_as_last_forward(self, ctx, buf, maskcent, mask_div, want_rgb, want_q, need_dist=False):
         """Did the (shared) context just run exactly this image + these hints (float32, as staged), producing at least
-        the outputs asked for?"""
+        the outputs asked for (RGB, quantised ab, the resident distribution)?"""
         last = ctx._wrapper_last
         if last is None or last[:3] != (float(maskcent), float(mask_div), False) or (want_rgb and not last[3]) or \
-                (want_q and not last[4]):
+                (want_q and not last[4]) or (need_dist and not last[5]):
             return False
         if not any(a is self.img_l_mc for a in ctx._wrapper_staged_l):
             l32 = np.ascontiguousarray(self.img_l_mc, dtype=np.float32).reshape(buf["L_mc"].shape)
@@ -445,7 +447,8 @@ class ColorizeImageB200Dist(ColorizeImageB200):
             ctx.set_dist_resident(True)                      # dist stays in HBM; pixels are fetched on demand
             # on a shared context keep the colour model's graph (same outputs requested -> no re-capture); the
             # distribution model itself publishes no RGB (reference :297-320 never sets output_rgb)
-            self._click(ctx, float(self.mask_cent), want_rgb=getattr(self, "_trunk", None) is not None, publish_rgb=False)
+            self._click(ctx, float(self.mask_cent), want_rgb=getattr(self, "_trunk", None) is not None, publish_rgb=False,
+                        need_dist=True)
         if self.materialize_full:
             self.dist_ab = np.repeat(np.repeat(self.dist_ab_64, 4, axis=1), 4, axis=2)
             self.dist_ab_full = np.zeros((self.AB, self.Xd, self.Xd))

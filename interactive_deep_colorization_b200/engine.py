@@ -52,6 +52,7 @@ class LhnContext(object):
         self._pinned = []
         # bookkeeping of the reference-facing wrappers that share this context (colorize_image.py: _click)
         self._wrapper_click, self._wrapper_staged_l, self._wrapper_last, self._wrapper_shared = None, [], None, False
+        self._dist_resident = False
         for k, v in (options or {}).items():
             self.set_option(k, v)
 
@@ -180,6 +181,7 @@ class LhnContext(object):
     def set_dist_resident(self, on=True):
         """Interactive mode: the dist head runs on every forward_host but stays on the device."""
         _lib.check(self.h, self.lib.idc_set_dist_resident(self.h, 1 if on else 0))
+        self._dist_resident = bool(on)
 
     def set_click(self, img=0, y4=-1, x4=0, K=0):
         """Announce the clicked pixel of the (H/4 x W/4) grid before forward_host: its pmf and K colour suggestions

@@ -120,6 +120,7 @@ class _FakeCtx(object):
         self.device = 0
         self._wrapper_click, self._wrapper_staged_l, self._wrapper_last, self._wrapper_shared = None, [], None, False
         self.calls, self.image_uploads, self.L = 0, 0, None
+        self._dist_resident = False
 
     def click_buffers(self, n=1, glob=False):
         X = self.H
@@ -133,7 +134,7 @@ class _FakeCtx(object):
         self.image_uploads += 1
 
     def set_dist_resident(self, on=True):
-        pass
+        self._dist_resident = bool(on)
 
     def set_click(self, *a):
         self.click = a
@@ -172,13 +173,20 @@ def test_shared_trunk_bookkeeping_without_a_gpu():
     cd = CI.ColorizeImageB200Dist(Xd=X, maskcent=True)
     cd.gpu_prepost = False
     cm.net, cm.net_set = _FakeNet(X), True
-    cd.share_trunk(cm)
     ctx = cm.net.ctx
-    assert ctx._wrapper_shared and cd.net is cm.net
     img = rs.randint(0, 256, (X, X, 3)).astype(np.uint8)
     cm.set_image(img); cd.set_image(img.copy())
     ab, m = np.zeros((2, X, X)), np.zeros((1, X, X))
     CI.put_point(ab, m, [5, 6], 1, [30, -20])
+    cm.net_forward(ab, m)                                          # BEFORE sharing: this forward carried no distribution
+    cd.share_trunk(cm)
+    assert ctx._wrapper_shared and cd.net is cm.net and ctx._dist_resident
+    cd.net_forward(ab, m)                                          # ... so the distribution model must not reuse it
+    assert ctx.calls == 2
+    ctx.calls = 0
+    rgb = cm.net_forward(ab, m)                                    # same hints again: answered from the dist model's forward
+    assert ctx.calls == 0 and ctx.image_uploads == 1
+    CI.put_point(ab, m, [2, 12], 1, [-40, 15])
     rgb = cm.net_forward(ab, m)
     assert ctx.calls == 1 and ctx.image_uploads == 1
     ret = cd.net_forward(ab.copy(), m.copy())                      # same image (another array object), same hints
